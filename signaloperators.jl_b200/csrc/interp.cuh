@@ -1,0 +1,192 @@
+// Elementwise program interpreter shared by every kernel (K1 and the fused
+// prologues/epilogues of the IIR and FIR kernels).
+//
+// Replaces, per output sample, the reference's recursive `frame(x,block,i)` walk:
+//   MapSignal.frame      src/mapsignal.jl:249-272
+//   SignalFunction frame src/functions.jl:53-60
+//   RampSignal frame     src/ramps.jl:56-72
+//   NumberBlock/PadBlock/CutBlock/AppendBlock/ArrayBlock frames
+//     src/numbers.jl:62-64, src/padding.jl:210-214, src/cutting.jl:217-218,
+//     src/appending.jl:89-90, src/arrays.jl:118-119
+// All index plumbing (offsets, valid lengths, pads) was resolved by the host
+// planner; the device only sees pure leaves evaluated at (n,c).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/signalops.h"
+
+namespace sigops {
+
+struct BufRef {            // one buffer of one instance
+    void*   ptr;
+    int64_t ld;
+    int32_t dtype;
+    int32_t nch;
+};
+
+// Everything a block needs to evaluate leaves for one instance.
+struct Env {
+    const BufRef* bufs;        // [nbuf] for this instance (shared memory copy)
+    const double* scalars;     // [nscalars] for this instance (global)
+};
+
+__device__ __forceinline__ double load_elem(const void* p, int dtype, int64_t i) {
+    if (dtype == SIGOPS_F64) return __ldg(reinterpret_cast<const double*>(p) + i);
+    if (dtype == SIGOPS_F32) return (double)__ldg(reinterpret_cast<const float*>(p) + i);
+    return (double)__ldg(reinterpret_cast<const long long*>(p) + i);
+}
+
+__device__ __forceinline__ double store_elem(void* p, int dtype, int64_t i, double v) {
+    if (dtype == SIGOPS_F64) { reinterpret_cast<double*>(p)[i] = v; return v; }
+    if (dtype == SIGOPS_F32) { float f = (float)v; reinterpret_cast<float*>(p)[i] = f; return (double)f; }
+    long long q = (long long)v; reinterpret_cast<long long*>(p)[i] = q; return (double)q;
+}
+
+__device__ __forceinline__ double apply_fn(int fn, double x, double a, double b) {
+    switch (fn) {
+        case SIGOPS_FN_SIN: return sin(x);
+        case SIGOPS_FN_COS: return cos(x);
+        case SIGOPS_FN_SAW: return x / 3.141592653589793 - 1.0;
+        case SIGOPS_FN_AFFINE_SIN: return a * sin(x) + b;
+        case SIGOPS_FN_AFFINE_COS: return a * cos(x) + b;
+        case SIGOPS_FN_IDENTITY: return x;
+        case SIGOPS_FN_SINRAMP: return sinpi(0.5 * x);
+    }
+    return 0.0;
+}
+
+// src/functions.jl:53-60 — evaluated in exactly this operation order
+__device__ __forceinline__ double gen_value(const sigops_instr& I, int64_t k) {
+    const double t = (double)k / I.d0;
+    if (I.flags & SIGOPS_FLAG_HAS_OMEGA) {
+        const double u = t * I.d1 + I.d2;
+        if (I.fn == SIGOPS_FN_SIN) return sinpi(2.0 * u);
+        return apply_fn(I.fn, 6.283185307179586 * fmod(u, 1.0), I.d3, I.d4);
+    }
+    if (I.fn == SIGOPS_FN_SIN) return sinpi(2.0 * (t + I.d2));
+    return apply_fn(I.fn, t + I.d2, I.d3, I.d4);
+}
+
+__device__ __forceinline__ double leaf_value(const sigops_instr& I, const Env& env,
+                                             const double* leafconst, int pc,
+                                             int64_t n, int c, double stageval) {
+    switch (I.leaf) {
+        case SIGOPS_LEAF_CONST:
+        case SIGOPS_LEAF_RMS:
+            return leafconst[pc];
+        case SIGOPS_LEAF_BUF: {
+            const BufRef b = env.bufs[I.buf];
+            int64_t idx = n + I.i0;
+            const int pad = (I.flags >> 1) & 3;
+            if (idx < 0 || idx >= I.i1) {
+                if (pad == SIGOPS_PAD_CONST || idx < 0 || I.i1 <= 0) return I.d0;
+                if (pad == SIGOPS_PAD_CYCLE) idx = idx % I.i1;
+                else if (pad == SIGOPS_PAD_MIRROR) {
+                    const int64_t cnt = idx / I.i1, rem = idx % I.i1;
+                    idx = (cnt & 1) ? (I.i1 - 1 - rem) : rem;
+                } else idx = I.i1 - 1;
+            }
+            const int ch = c * I.c_mul + I.c_off;
+            return load_elem(b.ptr, b.dtype, (int64_t)ch * b.ld + idx);
+        }
+        case SIGOPS_LEAF_CHANSUM: {
+            const BufRef b = env.bufs[I.buf];
+            const int64_t idx = n + I.i0;
+            if (idx < 0 || idx >= I.i1) return I.d0;
+            double s = load_elem(b.ptr, b.dtype, idx);
+            for (int ch = 1; ch < (int)I.i2; ++ch) s += load_elem(b.ptr, b.dtype, (int64_t)ch * b.ld + idx);
+            return s;
+        }
+        case SIGOPS_LEAF_GEN:
+            return gen_value(I, n + I.i0);
+        case SIGOPS_LEAF_RAMP_ON: {
+            const int64_t k = n + I.i0;
+            if (k > I.i1) return 1.0;
+            return apply_fn(I.fn, (double)(k - 1) / (double)I.i1, 0.0, 0.0);
+        }
+        case SIGOPS_LEAF_RAMP_OFF: {
+            const int64_t k = n + I.i0;
+            if (k <= I.i1) return 1.0;
+            return apply_fn(I.fn, 1.0 - (double)(k - I.i1) / (double)I.i2, 0.0, 0.0);
+        }
+        case SIGOPS_LEAF_STAGE:
+            return stageval;
+    }
+    return 0.0;
+}
+
+// Per-block preparation: copy the program to shared memory and fold the leaves
+// that do not depend on (n,c) (constants, Normpower divisors) into leafconst[].
+__device__ __forceinline__ void prepare_program(const sigops_instr* __restrict__ gprog, int len,
+                                                sigops_instr* sprog, double* leafconst,
+                                                const Env& env) {
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        sigops_instr I = gprog[i];
+        sprog[i] = I;
+        double v = 0.0;
+        if (I.leaf == SIGOPS_LEAF_CONST) v = I.d0;
+        // rms = sqrt(mean(x^2)) over the whole N x C matrix, src/filters.jl:304
+        else if (I.leaf == SIGOPS_LEAF_RMS) v = sqrt(env.scalars[I.buf] / I.d0);
+        leafconst[i] = v;
+    }
+}
+
+__device__ __forceinline__ double binop(int op, double a, double b) {
+    switch (op) {
+        case SIGOPS_OP_ADD: case SIGOPS_OP_POPADD: return a + b;
+        case SIGOPS_OP_SUB: case SIGOPS_OP_POPSUB: return a - b;
+        case SIGOPS_OP_MUL: case SIGOPS_OP_POPMUL: return a * b;
+        default: return a / b;
+    }
+}
+
+// Evaluate a program for V samples n[j] = n0 + j*nstride of channel c.
+// `stack` is this thread's spill area, laid out [depth][V] with stride
+// `sstride` doubles between consecutive slots (so neighbouring threads
+// interleave and stay bank-conflict free).
+template <int V>
+__device__ __forceinline__ void eval_program(const sigops_instr* sprog, const double* leafconst,
+                                             int len, const Env& env, int64_t n0, int64_t nstride,
+                                             int c, const double* stageval, double* acc,
+                                             double* stack, int sstride) {
+    int sp = 0;
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.0;
+    for (int pc = 0; pc < len; ++pc) {
+        const sigops_instr& I = sprog[pc];
+        const int op = I.op;
+        if (op <= SIGOPS_OP_DIV) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const double v = leaf_value(I, env, leafconst, pc, n0 + j * nstride, c,
+                                            stageval ? stageval[j] : 0.0);
+                acc[j] = (op == SIGOPS_OP_LOAD) ? v : binop(op, acc[j], v);
+            }
+        } else if (op == SIGOPS_OP_PUSH) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) stack[(sp * V + j) * sstride] = acc[j];
+            ++sp;
+        } else if (op <= SIGOPS_OP_POPDIV) {
+            --sp;
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[j] = binop(op, stack[(sp * V + j) * sstride], acc[j]);
+        } else if (op == SIGOPS_OP_NEG) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[j] = -acc[j];
+        } else if (op == SIGOPS_OP_CAST_F32) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[j] = (double)(float)acc[j];
+        } else if (op == SIGOPS_OP_CAST_I64) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[j] = (double)(long long)acc[j];
+        }
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace sigops

@@ -1,0 +1,267 @@
+// K3 — biquad-cascade (SOS, DF2T) filtering as a chunked parallel scan.
+//
+// Replaces DSP.jl's sequential `filt!(out, DF2TFilter{SOS}, x)` called per
+// channel per 4096-frame block at src/filters.jl:252-255 (recurrence restated
+// in SURVEY.md App. B.2), plus the two block copies around it
+// (src/filters.jl:240-244, 213-214).
+//
+// Parallel decomposition (the filter is linear and time-invariant):
+//   1. MAIN   every channel is cut into chunks of L frames; each lane runs the
+//             cascade over one chunk from ZERO state (zero-state response) and
+//             records its final state.  Lanes of a warp own 32 consecutive chunks
+//             of one channel; data moves through a per-warp 32x32 shared-memory
+//             tile so every global access is a coalesced 256-byte row.
+//   2. CARRY  s_in[k] = s_zs[k-1] + A^L s_in[k-1]   (cross-chunk / cross-block
+//             carry of the 2M-vector state; A^L is the cascade's L-step state
+//             transition matrix, precomputed on the host).
+//   3. FIX    chunk k >= 1 adds the zero-input response of s_in[k] to its first
+//             Wc frames, where Wc is the number of frames after which that
+//             response has decayed below 2^-64 of its peak (Wc = L if it never
+//             does).  MAIN leaves those frames un-finalised; FIX applies the
+//             fused epilogue to them.
+// Superposition makes 1+3 equal to the sequential filter up to rounding.
+//
+// Roofline: 16 B/sample HBM (8 in + 8 out); 5 FP64 instructions per section per
+// sample ("FP64 pipe ~ HBM").
+#pragma once
+#include "interp.cuh"
+
+namespace sigops {
+
+constexpr int kIirWarps = 4;
+constexpr int kIirThreads = kIirWarps * 32;
+constexpr int kIirV = 4;
+constexpr int kIirMaxSections = 8;
+constexpr int kTilePitch = 33;
+
+struct IirParams {
+    const sigops_instr* instrs;
+    const BufRef* bufrefs;     // [ninst][nbuf]
+    double* scalars;           // [ninst][nscalars]
+    int nbuf, nscalars;
+    int out_buf, sumsq_slot;
+    int in_prog_start, in_prog_len;
+    int epi_prog_start, epi_prog_len;
+    int plain_in_buf;          // >= 0: input program is a bare zero-padded buffer load
+    int64_t plain_in_len;
+    int nch;                   // channels (rows) per instance
+    int blocks_per_row;
+    int64_t N, L, Wc;          // frames, chunk length, un-finalised prefix (both multiples of 32)
+    int64_t slots_per_row;     // blocks_per_row * kIirThreads
+    double* state_zs;          // [2M][rows*slots_per_row]  MAIN out
+    double* state_in;          // [2M][rows*slots_per_row]  CARRY out, FIX in
+    int M;
+    double gain;
+    double coef[kIirMaxSections][5];
+};
+
+enum { IIR_MAIN = 0, IIR_FIX = 1 };
+
+template <int M>
+struct Cascade {
+    double b0[M], b1[M], b2[M], a1[M], a2[M];
+    double s1[M], s2[M];
+    __device__ __forceinline__ void init(const IirParams& P) {
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            b0[j] = P.coef[j][0]; b1[j] = P.coef[j][1]; b2[j] = P.coef[j][2];
+            a1[j] = P.coef[j][3]; a2[j] = P.coef[j][4];
+            s1[j] = 0.0; s2[j] = 0.0;
+        }
+    }
+    // DSP.jl `_filt!` for SecondOrderSections (DF2T), SURVEY.md App. B.2
+    __device__ __forceinline__ double step(double x) {
+        double y = x;
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            const double xi = y;
+            y = fma(b0[j], xi, s1[j]);
+            s1[j] = fma(-a1[j], y, fma(b1[j], xi, s2[j]));
+            s2[j] = fma(-a2[j], y, b2[j] * xi);
+        }
+        return y;
+    }
+    // same with x == 0 entering the first section
+    __device__ __forceinline__ double step_zero_input() {
+        double y = s1[0];
+        s1[0] = fma(-a1[0], y, s2[0]);
+        s2[0] = -a2[0] * y;
+#pragma unroll
+        for (int j = 1; j < M; ++j) {
+            const double xi = y;
+            y = fma(b0[j], xi, s1[j]);
+            s1[j] = fma(-a1[j], y, fma(b1[j], xi, s2[j]));
+            s2[j] = fma(-a2[j], y, b2[j] * xi);
+        }
+        return y;
+    }
+};
+
+template <int M, int MODE>
+__global__ void __launch_bounds__(kIirThreads)
+k_iir(const __grid_constant__ IirParams P) {
+    __shared__ sigops_instr sprog_in[SIGOPS_MAX_PROG];
+    __shared__ sigops_instr sprog_epi[SIGOPS_MAX_PROG];
+    __shared__ double lc_in[SIGOPS_MAX_PROG], lc_epi[SIGOPS_MAX_PROG];
+    __shared__ BufRef sbufs[32];
+    __shared__ double tiles[kIirWarps][32 * kTilePitch];
+    extern __shared__ double stack[];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = blockIdx.x / P.blocks_per_row;
+    const int brow = blockIdx.x % P.blocks_per_row;
+    const int inst = (int)(row / P.nch), c = (int)(row % P.nch);
+
+    for (int i = threadIdx.x; i < P.nbuf; i += blockDim.x) sbufs[i] = P.bufrefs[(size_t)inst * P.nbuf + i];
+    Env env{sbufs, P.scalars + (size_t)inst * P.nscalars};
+    prepare_program(P.instrs + P.in_prog_start, P.in_prog_len, sprog_in, lc_in, env);
+    prepare_program(P.instrs + P.epi_prog_start, P.epi_prog_len, sprog_epi, lc_epi, env);
+    __syncthreads();
+
+    double* tile = tiles[warp];
+    const int64_t chunk0 = (int64_t)brow * kIirThreads + warp * 32;  // first chunk of this warp
+    const int64_t mychunk = chunk0 + lane;
+    const int64_t slot = row * P.slots_per_row + mychunk;
+    const int64_t nslots = (int64_t)gridDim.x / P.blocks_per_row * P.slots_per_row;
+    if (chunk0 * P.L >= P.N) return;      // whole warp past the end (warp-uniform)
+
+    Cascade<M> f;
+    f.init(P);
+    if (MODE == IIR_FIX) {
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            f.s1[j] = P.state_in[(2 * j) * nslots + slot];
+            f.s2[j] = P.state_in[(2 * j + 1) * nslots + slot];
+        }
+    }
+
+    const BufRef ob = sbufs[P.out_buf];
+    const int64_t nsub_all = P.L / 32, nsub_raw = P.Wc / 32;
+    const int64_t nsub = (MODE == IIR_FIX) ? nsub_raw : nsub_all;
+    double ss = 0.0;
+
+    for (int64_t s = 0; s < nsub; ++s) {
+        // ---- load phase: rows of the tile = chunks, columns = 32 consecutive frames
+#pragma unroll 1
+        for (int r = 0; r < 32; r += kIirV) {
+            const int64_t n0 = (chunk0 + r) * P.L + s * 32 + lane;
+            double v[kIirV];
+            if (MODE == IIR_MAIN) {
+                if (P.plain_in_buf >= 0) {
+                    const BufRef ib = sbufs[P.plain_in_buf];
+#pragma unroll
+                    for (int j = 0; j < kIirV; ++j) {
+                        const int64_t n = n0 + j * P.L;
+                        v[j] = (n < P.plain_in_len) ? load_elem(ib.ptr, ib.dtype, (int64_t)c * ib.ld + n) : 0.0;
+                    }
+                } else {
+                    eval_program<kIirV>(sprog_in, lc_in, P.in_prog_len, env, n0, P.L, c, nullptr, v,
+                                        stack + threadIdx.x, kIirThreads);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < kIirV; ++j) {
+                    const int64_t n = n0 + j * P.L;
+                    v[j] = (n < P.N && chunk0 + r + j >= 1)
+                               ? load_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + n) : 0.0;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kIirV; ++j) tile[(r + j) * kTilePitch + lane] = v[j];
+        }
+        __syncwarp();
+
+        // ---- compute phase: lane = chunk, 32 sequential frames
+        {
+            double* myrow = tile + lane * kTilePitch;
+            if (MODE == IIR_MAIN) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) myrow[k] = f.step(myrow[k]) * P.gain;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) myrow[k] = fma(f.step_zero_input(), P.gain, myrow[k]);
+            }
+        }
+        __syncwarp();
+
+        // ---- store phase
+#pragma unroll 1
+        for (int r = 0; r < 32; r += kIirV) {
+            const int64_t n0 = (chunk0 + r) * P.L + s * 32 + lane;
+            double y[kIirV], o[kIirV];
+#pragma unroll
+            for (int j = 0; j < kIirV; ++j) y[j] = tile[(r + j) * kTilePitch + lane];
+            if (P.epi_prog_len > 0)
+                eval_program<kIirV>(sprog_epi, lc_epi, P.epi_prog_len, env, n0, P.L, c, y, o,
+                                    stack + threadIdx.x, kIirThreads);
+            else {
+#pragma unroll
+                for (int j = 0; j < kIirV; ++j) o[j] = y[j];
+            }
+#pragma unroll
+            for (int j = 0; j < kIirV; ++j) {
+                const int64_t n = n0 + j * P.L;
+                const int64_t chunk = chunk0 + r + j;
+                if (n >= P.N) continue;
+                if (MODE == IIR_MAIN) {
+                    const bool unfinished = (chunk >= 1) && (s < nsub_raw);
+                    if (unfinished) {
+                        store_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + n, y[j]);
+                    } else {
+                        const double w = store_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + n, o[j]);
+                        ss += w * w;
+                    }
+                } else if (chunk >= 1) {
+                    const double w = store_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + n, o[j]);
+                    ss += w * w;
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    if (MODE == IIR_MAIN) {
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            P.state_zs[(2 * j) * nslots + slot] = f.s1[j];
+            P.state_zs[(2 * j + 1) * nslots + slot] = f.s2[j];
+        }
+    }
+    if (P.sumsq_slot >= 0) {
+        ss = warp_sum(ss);
+        if (lane == 0) atomicAdd(P.scalars + (size_t)inst * P.nscalars + P.sumsq_slot, ss);
+    }
+}
+
+// CARRY: one thread per row walks its chunks in order.
+//   s_in[0] = 0;  s_in[k] = s_zs[k-1] + AL * s_in[k-1]
+// `AL` is the (2M x 2M) L-step state transition matrix (row-major) or nullptr
+// when the zero-input response has fully decayed within one chunk (Wc < L).
+struct CarryParams {
+    const double* state_zs;
+    double* state_in;
+    const double* AL;
+    int64_t nrows, slots_per_row, nchunks;
+    int M2;     // 2M
+};
+
+__global__ void k_iir_carry(const CarryParams P) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= P.nrows) return;
+    const int64_t nslots = P.nrows * P.slots_per_row;
+    double s[2 * kIirMaxSections], t[2 * kIirMaxSections];
+    for (int i = 0; i < P.M2; ++i) s[i] = 0.0;
+    for (int64_t k = 0; k < P.nchunks; ++k) {
+        const int64_t slot = row * P.slots_per_row + k;
+        for (int i = 0; i < P.M2; ++i) P.state_in[i * nslots + slot] = s[i];
+        for (int i = 0; i < P.M2; ++i) {
+            double a = P.state_zs[i * nslots + slot];
+            if (P.AL)
+                for (int j = 0; j < P.M2; ++j) a = fma(P.AL[i * P.M2 + j], s[j], a);
+            t[i] = a;
+        }
+        for (int i = 0; i < P.M2; ++i) s[i] = t[i];
+    }
+}
+
+}  // namespace sigops

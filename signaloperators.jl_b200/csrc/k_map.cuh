@@ -1,0 +1,85 @@
+// K1 — fused elementwise / generator kernel.
+//
+// One launch materialises a whole MAP stage: every piece (Append segment /
+// AddChannel channel group) of the stage's output, all channels, all instances
+// of the batch.  Replaces the `sink!` block loop + `sink_helper!` inner loop
+// (src/sink.jl:225-267) for graphs without filters, and the three memory
+// passes of `initblock(::NormedSignal)` (src/filters.jl:296-309): the sum of
+// squares is accumulated while the producer stores, the division by the RMS is
+// a leaf of the consumer's program.
+//
+// HBM-bound: 8(k+1) bytes per output sample for k buffer leaves.
+// Layout: thread t of a 256-thread block owns frames t, t+256, t+512, t+768 of a
+// 1024-frame tile, so every warp access is a fully coalesced 256-byte row.
+#pragma once
+#include "interp.cuh"
+
+namespace sigops {
+
+constexpr int kMapThreads = 256;
+constexpr int kMapV = 4;
+constexpr int kMapTile = kMapThreads * kMapV;
+constexpr int kMaxPieces = 64;
+constexpr int kMaxBufs = 32;
+
+struct MapParams {
+    const sigops_instr* instrs;     // whole plan's instruction array (device)
+    const BufRef* bufrefs;          // [ninst][nbuf]
+    double* scalars;                // [ninst][nscalars]
+    int nbuf, nscalars;
+    int out_buf, sumsq_slot, out_nch;
+    int n_pieces;
+    sigops_piece pieces[kMaxPieces];
+    int tile_prefix[kMaxPieces + 1];
+};
+
+__global__ void __launch_bounds__(kMapThreads)
+k_map(const __grid_constant__ MapParams P) {
+    __shared__ sigops_instr sprog[SIGOPS_MAX_PROG];
+    __shared__ double leafconst[SIGOPS_MAX_PROG];
+    __shared__ BufRef sbufs[kMaxBufs];
+    __shared__ double red[kMapThreads / 32];
+    extern __shared__ double stack[];
+
+    const int inst = blockIdx.z, c = blockIdx.y;
+    int p = 0;
+    while (p + 1 < P.n_pieces && (int)blockIdx.x >= P.tile_prefix[p + 1]) ++p;
+    const sigops_piece pc = P.pieces[p];
+    if (c < pc.ch_start || c >= pc.ch_start + pc.ch_count) return;
+
+    for (int i = threadIdx.x; i < P.nbuf; i += blockDim.x) sbufs[i] = P.bufrefs[(size_t)inst * P.nbuf + i];
+    Env env{sbufs, P.scalars + (size_t)inst * P.nscalars};
+    prepare_program(P.instrs + pc.prog_start, pc.prog_len, sprog, leafconst, env);
+    __syncthreads();
+
+    const int64_t tile = (int64_t)blockIdx.x - P.tile_prefix[p];
+    const int64_t n0 = pc.out_start + tile * kMapTile + threadIdx.x;
+    const int64_t nend = pc.out_start + pc.out_len;
+
+    double acc[kMapV];
+    eval_program<kMapV>(sprog, leafconst, pc.prog_len, env, n0, kMapThreads, c, nullptr, acc,
+                        stack + threadIdx.x, kMapThreads);
+
+    const BufRef ob = sbufs[P.out_buf];
+    double ss = 0.0;
+#pragma unroll
+    for (int j = 0; j < kMapV; ++j) {
+        const int64_t n = n0 + (int64_t)j * kMapThreads;
+        if (n < nend) {
+            const double v = store_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + n, acc[j]);
+            ss += v * v;
+        }
+    }
+    if (P.sumsq_slot >= 0) {
+        ss = warp_sum(ss);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < kMapThreads / 32; ++w) t += red[w];
+            atomicAdd(P.scalars + (size_t)inst * P.nscalars + P.sumsq_slot, t);
+        }
+    }
+}
+
+}  // namespace sigops

@@ -1,0 +1,1186 @@
+// libsignalops_cuda.so — host runtime behind the C ABI of include/signalops.h.
+//
+// Plan parsing/validation, per-device workspaces, stage launch order, batch
+// sharding over devices (no collectives: instances are independent, SURVEY.md
+// §8e) and the host<->device pipeline of `sigops_plan_run`.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/signalops.h"
+#include "k_fir.cuh"
+#include "k_iir.cuh"
+#include "k_map.cuh"
+
+static_assert(sizeof(sigops_instr) == 80, "ABI: sigops_instr");
+static_assert(sizeof(sigops_piece) == 32, "ABI: sigops_piece");
+static_assert(sizeof(sigops_stage) == 128, "ABI: sigops_stage");
+static_assert(sizeof(sigops_plan_header) == 48, "ABI: sigops_plan_header");
+static_assert(sizeof(sigops_bufdesc) == 16, "ABI: sigops_bufdesc");
+
+using namespace sigops;
+
+namespace {
+
+thread_local std::string g_tls_error = "";
+
+struct Failure {
+    int code;
+    std::string msg;
+};
+
+[[noreturn]] void fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    throw Failure{code, buf};
+}
+
+#define CUDA_OK(expr)                                                                       \
+    do {                                                                                    \
+        cudaError_t e__ = (expr);                                                           \
+        if (e__ != cudaSuccess)                                                             \
+            fail(e__ == cudaErrorMemoryAllocation ? SIGOPS_ERR_NOMEM : SIGOPS_ERR_CUDA,    \
+                 "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__,   \
+                 cudaGetErrorString(e__));                                                  \
+    } while (0)
+
+size_t elem_size(int dtype) { return dtype == SIGOPS_F32 ? 4 : 8; }
+int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// Grow-only device arena (one per pipeline slot); reset at the start of a wave.
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0, used = 0;
+    void reset() { used = 0; }
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (base) CUDA_OK(cudaFree(base));
+        base = nullptr;
+        cap = 0;
+        CUDA_OK(cudaMalloc(&base, bytes));
+        cap = bytes;
+    }
+    void* take(size_t bytes) {
+        size_t off = (used + 255) & ~size_t(255);
+        if (off + bytes > cap) fail(SIGOPS_ERR_NOMEM, "internal: arena overflow (%zu > %zu)", off + bytes, cap);
+        used = off + bytes;
+        return base + off;
+    }
+    void release() {
+        if (base) cudaFree(base);
+        base = nullptr;
+        cap = used = 0;
+    }
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    Arena arena;
+    void* pinned = nullptr;      // staging for the BufRef table
+    size_t pinned_cap = 0;
+    std::vector<char> last_table; // contents last uploaded (skip identical re-uploads)
+    void* last_table_dev = nullptr;
+    cudaEvent_t ev[6] = {};
+};
+
+struct Device {
+    int ordinal = 0;
+    int sm_count = 148;
+    Slot slots[2];
+};
+
+// ---- per-stage derived data ---------------------------------------------------
+
+struct IirDerived {
+    int M = 0;
+    int64_t W = 0;                 // decay length of the zero-input response (frames)
+    bool plain_in = false;
+    int plain_buf = -1;
+    int64_t plain_len = 0;
+};
+
+struct FirDerived {
+    std::vector<int64_t> xi0;
+    std::vector<double> phi;
+    int dpad = 0, pmax = 0;
+    int in_buf = -1;
+    int64_t in_len = 0;
+};
+
+struct StageRT {
+    sigops_stage st;
+    IirDerived iir;
+    FirDerived fir;
+};
+
+struct PlanDev {               // device-resident constants of a plan
+    bool ready = false;
+    sigops_instr* instrs = nullptr;
+    double* blob = nullptr;
+    std::vector<int64_t*> xi0;  // per stage
+    std::vector<double*> phi;
+};
+
+}  // namespace
+
+struct sigops_ctx {
+    std::vector<Device> devs;
+    std::string err;
+    std::mutex mu;
+    size_t ws_budget = size_t(16) << 30;
+};
+
+struct sigops_plan {
+    sigops_ctx* ctx = nullptr;
+    sigops_plan_header h{};
+    std::vector<sigops_bufdesc> bufs;
+    std::vector<sigops_tabledesc> tables;
+    std::vector<sigops_instr> instrs;
+    std::vector<sigops_piece> pieces;
+    std::vector<StageRT> stages;
+    std::vector<double> blob;
+    std::vector<PlanDev> dev;
+    int nbuf() const { return (int)bufs.size(); }
+    int max_stack = 0;
+};
+
+namespace {
+
+// ---- plan validation ----------------------------------------------------------
+
+int program_stack_depth(const sigops_plan& p, int start, int len, bool allow_stage, const char* what) {
+    if (len < 0 || start < 0 || (size_t)start + len > p.instrs.size())
+        fail(SIGOPS_ERR_INVALID, "%s: program range [%d,+%d) outside the instruction array", what, start, len);
+    if (len > SIGOPS_MAX_PROG)
+        fail(SIGOPS_ERR_UNSUPPORTED, "%s: program of %d instructions exceeds SIGOPS_MAX_PROG=%d", what, len, SIGOPS_MAX_PROG);
+    int sp = 0, maxsp = 0;
+    for (int i = 0; i < len; ++i) {
+        const sigops_instr& I = p.instrs[start + i];
+        if (I.op < SIGOPS_OP_LOAD || I.op > SIGOPS_OP_CAST_I64) fail(SIGOPS_ERR_INVALID, "%s: bad opcode %d", what, I.op);
+        if (i == 0 && I.op != SIGOPS_OP_LOAD) fail(SIGOPS_ERR_INVALID, "%s: program must start with LOAD", what);
+        if (I.op <= SIGOPS_OP_DIV) {
+            switch (I.leaf) {
+                case SIGOPS_LEAF_CONST: break;
+                case SIGOPS_LEAF_BUF:
+                case SIGOPS_LEAF_CHANSUM: {
+                    if (I.buf < 0 || I.buf >= p.nbuf()) fail(SIGOPS_ERR_INVALID, "%s: leaf reads buffer %d of %d", what, I.buf, p.nbuf());
+                    const sigops_bufdesc& b = p.bufs[I.buf];
+                    if (I.i1 > b.nframes) fail(SIGOPS_ERR_INVALID, "%s: leaf valid length %lld exceeds buffer frames %lld", what, (long long)I.i1, (long long)b.nframes);
+                    if (I.leaf == SIGOPS_LEAF_CHANSUM && (I.i2 < 1 || I.i2 > b.nchannels)) fail(SIGOPS_ERR_INVALID, "%s: CHANSUM over %lld channels of %d", what, (long long)I.i2, b.nchannels);
+                    if (I.leaf == SIGOPS_LEAF_BUF && (I.c_mul < 0 || I.c_mul > 1 || I.c_off < -65536)) fail(SIGOPS_ERR_INVALID, "%s: bad channel map", what);
+                    break;
+                }
+                case SIGOPS_LEAF_GEN:
+                    if (!(I.d0 > 0)) fail(SIGOPS_ERR_INVALID, "%s: generator needs a positive frame rate", what);
+                    if (I.fn < SIGOPS_FN_SIN || I.fn > SIGOPS_FN_IDENTITY) fail(SIGOPS_ERR_UNSUPPORTED, "%s: generator fn %d", what, I.fn);
+                    break;
+                case SIGOPS_LEAF_RAMP_ON:
+                case SIGOPS_LEAF_RAMP_OFF:
+                    if (I.fn != SIGOPS_FN_SINRAMP && I.fn != SIGOPS_FN_IDENTITY) fail(SIGOPS_ERR_UNSUPPORTED, "%s: ramp fn %d", what, I.fn);
+                    if ((I.leaf == SIGOPS_LEAF_RAMP_ON ? I.i1 : I.i2) < 1) fail(SIGOPS_ERR_INVALID, "%s: ramp length must be >= 1", what);
+                    break;
+                case SIGOPS_LEAF_RMS:
+                    if (I.buf < 0 || I.buf >= (int)p.h.n_scalars) fail(SIGOPS_ERR_INVALID, "%s: scalar slot %d of %u", what, I.buf, p.h.n_scalars);
+                    break;
+                case SIGOPS_LEAF_STAGE:
+                    if (!allow_stage) fail(SIGOPS_ERR_INVALID, "%s: LEAF_STAGE outside an epilogue", what);
+                    break;
+                default: fail(SIGOPS_ERR_INVALID, "%s: bad leaf kind %d", what, I.leaf);
+            }
+        } else if (I.op == SIGOPS_OP_PUSH) {
+            if (++sp > SIGOPS_MAX_STACK) fail(SIGOPS_ERR_UNSUPPORTED, "%s: expression nests deeper than SIGOPS_MAX_STACK", what);
+            maxsp = std::max(maxsp, sp);
+        } else if (I.op <= SIGOPS_OP_POPDIV) {
+            if (--sp < 0) fail(SIGOPS_ERR_INVALID, "%s: POP on empty stack", what);
+        }
+    }
+    if (sp != 0) fail(SIGOPS_ERR_INVALID, "%s: unbalanced PUSH/POP", what);
+    return maxsp;
+}
+
+// zero-input decay length of the cascade: the frame after which neither the
+// output nor any state exceeds 2^-64 of its peak, for every unit initial state.
+int64_t decay_length(const double (*c)[5], int M, double g, int64_t limit) {
+    const int S = 2 * M;
+    std::vector<double> st((size_t)S * S, 0.0);
+    for (int b = 0; b < S; ++b) st[(size_t)b * S + b] = 1.0;
+    double peak = 1.0;
+    int64_t last = 0;
+    const double thresh = std::ldexp(1.0, -64);
+    for (int64_t k = 0; k < limit; ++k) {
+        double norm = 0.0;
+        for (int b = 0; b < S; ++b) {
+            double* s = &st[(size_t)b * S];
+            double y = 0.0;
+            for (int j = 0; j < M; ++j) {
+                const double xi = y;
+                y = s[2 * j] + c[j][0] * xi;
+                s[2 * j] = s[2 * j + 1] + c[j][1] * xi - c[j][3] * y;
+                s[2 * j + 1] = c[j][2] * xi - c[j][4] * y;
+                norm = std::max(norm, std::max(std::fabs(s[2 * j]), std::fabs(s[2 * j + 1])));
+            }
+            norm = std::max(norm, std::fabs(y));
+        }
+        if (!(norm == norm) || std::isinf(norm)) return limit;   // unstable filter: never decays
+        peak = std::max(peak, norm);
+        if (norm > thresh * peak) last = k + 1;
+        else if (k - last > 256) break;
+    }
+    return std::min(limit, last + 1);
+}
+
+// L-step state transition matrix of the cascade (row-major S x S).
+std::vector<double> transition_matrix(const double (*c)[5], int M, int64_t L) {
+    const int S = 2 * M;
+    std::vector<double> AL((size_t)S * S);
+    for (int b = 0; b < S; ++b) {
+        std::vector<double> s(S, 0.0);
+        s[b] = 1.0;
+        for (int64_t k = 0; k < L; ++k) {
+            double y = 0.0;
+            for (int j = 0; j < M; ++j) {
+                const double xi = y;
+                y = s[2 * j] + c[j][0] * xi;
+                s[2 * j] = s[2 * j + 1] + c[j][1] * xi - c[j][3] * y;
+                s[2 * j + 1] = c[j][2] * xi - c[j][4] * y;
+            }
+        }
+        for (int i = 0; i < S; ++i) AL[(size_t)i * S + b] = s[i];
+    }
+    return AL;
+}
+
+void derive_iir(sigops_plan& p, StageRT& s, int idx) {
+    const sigops_stage& st = s.st;
+    char what[64];
+    snprintf(what, sizeof what, "stage %d (IIR)", idx);
+    if (st.n_sections < 1 || st.n_sections > kIirMaxSections)
+        fail(SIGOPS_ERR_UNSUPPORTED, "%s: %d biquad sections (1..%d supported per stage)", what, st.n_sections, kIirMaxSections);
+    if (st.coef_table < 0 || st.coef_table >= (int)p.tables.size() || p.tables[st.coef_table].count != 5 * st.n_sections)
+        fail(SIGOPS_ERR_INVALID, "%s: coefficient table must hold 5*M doubles", what);
+    if (st.n_in != st.n_out) fail(SIGOPS_ERR_INVALID, "%s: n_in != n_out", what);
+    s.iir.M = st.n_sections;
+    const double* t = p.blob.data() + p.tables[st.coef_table].offset;
+    double c[kIirMaxSections][5];
+    for (int j = 0; j < st.n_sections; ++j)
+        for (int k = 0; k < 5; ++k) c[j][k] = t[j * 5 + k];
+    s.iir.W = decay_length(c, st.n_sections, st.gain, std::max<int64_t>(32, std::min<int64_t>(st.n_out, 1 << 18)));
+    if (st.in_prog_len == 1) {
+        const sigops_instr& I = p.instrs[st.in_prog_start];
+        if (I.op == SIGOPS_OP_LOAD && I.leaf == SIGOPS_LEAF_BUF && I.i0 == 0 && I.c_mul == 1 && I.c_off == 0 &&
+            ((I.flags >> 1) & 3) == SIGOPS_PAD_CONST && I.d0 == 0.0) {
+            s.iir.plain_in = true;
+            s.iir.plain_buf = I.buf;
+            s.iir.plain_len = I.i1;
+        }
+    }
+}
+
+void derive_fir(sigops_plan& p, StageRT& s, int idx) {
+    const sigops_stage& st = s.st;
+    char what[64];
+    snprintf(what, sizeof what, "stage %d (FIR)", idx);
+    if (st.taps_per_phase < 1 || st.n_phases < 1) fail(SIGOPS_ERR_INVALID, "%s: empty filter bank", what);
+    if (st.taps_per_phase > 1024) fail(SIGOPS_ERR_UNSUPPORTED, "%s: %d taps per phase (<= 1024 supported)", what, st.taps_per_phase);
+    auto check_table = [&](int id, const char* nm) {
+        if (id < 0 || id >= (int)p.tables.size() || p.tables[id].count != (int64_t)st.n_phases * st.taps_per_phase)
+            fail(SIGOPS_ERR_INVALID, "%s: %s table must hold n_phases*taps_per_phase doubles", what, nm);
+    };
+    check_table(st.pfb_table, "pfb");
+    if (st.dpfb_table >= 0) check_table(st.dpfb_table, "dpfb");
+    if (st.input_deficit < 1) fail(SIGOPS_ERR_INVALID, "%s: input_deficit must be >= 1", what);
+    if (st.in_prog_len != 1) fail(SIGOPS_ERR_UNSUPPORTED, "%s: input must be a materialised buffer", what);
+    const sigops_instr& I = p.instrs[st.in_prog_start];
+    if (!(I.op == SIGOPS_OP_LOAD && I.leaf == SIGOPS_LEAF_BUF && I.i0 == 0 && I.c_mul == 1 && I.c_off == 0 &&
+          ((I.flags >> 1) & 3) == SIGOPS_PAD_CONST && I.d0 == 0.0))
+        fail(SIGOPS_ERR_UNSUPPORTED, "%s: input must be a bare zero-padded buffer load", what);
+    s.fir.in_buf = I.buf;
+    s.fir.in_len = I.i1;
+
+    // Replay the kernel's index recurrence (DSP.jl stream_filt.jl `filt!`/`update`).
+    const int64_t nout = st.n_out;
+    const int64_t padded = round_up(std::max<int64_t>(nout, 1), kFirT);
+    s.fir.xi0.resize(padded);
+    s.fir.phi.resize(padded);
+    int64_t x = st.input_deficit;              // 1-based index of the newest sample
+    if (st.fir_kind == SIGOPS_FIR_ARBITRARY) {
+        if (st.dpfb_table < 0) fail(SIGOPS_ERR_INVALID, "%s: arbitrary-rate kernel needs the derivative bank", what);
+        if (!(st.rate > 0)) fail(SIGOPS_ERR_INVALID, "%s: rate must be positive", what);
+        const double nphi = (double)st.n_phases;
+        const double delta = nphi / st.rate;
+        double acc = st.phase0;
+        if (!(acc >= 1.0 && acc < nphi + 1.0)) fail(SIGOPS_ERR_INVALID, "%s: phase accumulator outside [1,Nphi+1)", what);
+        for (int64_t m = 0; m < nout; ++m) {
+            s.fir.xi0[m] = x - 1;
+            s.fir.phi[m] = acc;
+            acc += delta;
+            if (acc > nphi) {
+                x += (int64_t)std::floor((acc - 1.0) / nphi);
+                acc = std::fmod(acc - 1.0, nphi) + 1.0;
+            }
+        }
+    } else if (st.fir_kind == SIGOPS_FIR_RATIONAL) {
+        const int p_ = st.interpolation, q = st.decimation;
+        if (p_ != st.n_phases || q < 1) fail(SIGOPS_ERR_INVALID, "%s: rational kernel needs n_phases == interpolation", what);
+        int64_t ph = (int64_t)st.phase0;
+        if (ph < 1 || ph > p_) fail(SIGOPS_ERR_INVALID, "%s: phase index outside 1..p", what);
+        const int step = q % p_;
+        for (int64_t m = 0; m < nout; ++m) {
+            s.fir.xi0[m] = x - 1;
+            s.fir.phi[m] = (double)ph;
+            x += (ph + q - 1) / p_;
+            const int64_t v = ph + step;
+            ph = v > p_ ? v - p_ : v;
+        }
+    } else if (st.fir_kind == SIGOPS_FIR_DECIMATOR) {
+        if (st.n_phases != 1 || st.decimation < 1) fail(SIGOPS_ERR_INVALID, "%s: decimator needs one phase", what);
+        for (int64_t m = 0; m < nout; ++m) {
+            s.fir.xi0[m] = x - 1;
+            s.fir.phi[m] = 1.0;
+            x += st.decimation;
+        }
+    } else
+        fail(SIGOPS_ERR_INVALID, "%s: unknown FIR kind %d", what, st.fir_kind);
+    for (int64_t m = nout; m < padded; ++m) {
+        s.fir.xi0[m] = nout ? s.fir.xi0[nout - 1] : 0;
+        s.fir.phi[m] = 1.0;
+    }
+    int64_t dpad = 0, span = 0;
+    for (int64_t m = 0; m + kFirR - 1 < padded; ++m) dpad = std::max(dpad, s.fir.xi0[m + kFirR - 1] - s.fir.xi0[m]);
+    for (int64_t m = 0; m < padded; m += kFirT) span = std::max(span, s.fir.xi0[m + kFirT - 1] - s.fir.xi0[m]);
+    s.fir.dpad = (int)dpad;
+    s.fir.pmax = (int)(span + st.taps_per_phase);
+    const size_t smem = ((size_t)kFirT * (st.taps_per_phase + 2 * dpad) +
+                         (size_t)std::max<int64_t>(s.fir.pmax, kFirT) * kFirRowPitch +
+                         (size_t)SIGOPS_MAX_STACK * 2 * kFirThreads) * sizeof(double);
+    if (smem > 220 * 1024)
+        fail(SIGOPS_ERR_UNSUPPORTED, "%s: resampling ratio %g with %d taps/phase needs %zu bytes of shared memory per block",
+             what, st.rate, st.taps_per_phase, smem);
+}
+
+void parse_plan(sigops_plan& p, const void* bytes, size_t nbytes) {
+    const char* cur = (const char*)bytes;
+    const char* end = cur + nbytes;
+    auto take = [&](void* dst, size_t n, const char* what) {
+        if ((size_t)(end - cur) < n) fail(SIGOPS_ERR_INVALID, "plan truncated while reading %s", what);
+        memcpy(dst, cur, n);
+        cur += n;
+    };
+    take(&p.h, sizeof p.h, "header");
+    if (p.h.magic != SIGOPS_MAGIC) fail(SIGOPS_ERR_INVALID, "bad plan magic 0x%08x", p.h.magic);
+    if (p.h.version != SIGOPS_PLAN_VERSION) fail(SIGOPS_ERR_INVALID, "plan version %u, library speaks %u", p.h.version, SIGOPS_PLAN_VERSION);
+    const uint64_t nb = (uint64_t)p.h.n_inputs + p.h.n_temps + p.h.n_outputs;
+    if (nb == 0 || nb > kMaxBufs) fail(SIGOPS_ERR_UNSUPPORTED, "plan uses %llu buffers (1..%d supported)", (unsigned long long)nb, kMaxBufs);
+    if (p.h.n_outputs < 1) fail(SIGOPS_ERR_INVALID, "plan has no output");
+    if (p.h.n_stages < 1 || p.h.n_stages > 4096) fail(SIGOPS_ERR_INVALID, "plan has %u stages", p.h.n_stages);
+    if (p.h.n_instrs > (1u << 20) || p.h.n_pieces > (1u << 20) || p.h.n_tables > (1u << 16) ||
+        p.h.n_table_doubles > (uint64_t(1) << 31) || p.h.n_scalars > 4096)
+        fail(SIGOPS_ERR_INVALID, "plan section counts out of range");
+    p.bufs.resize(nb);
+    take(p.bufs.data(), nb * sizeof(sigops_bufdesc), "buffer descriptors");
+    p.tables.resize(p.h.n_tables);
+    take(p.tables.data(), p.h.n_tables * sizeof(sigops_tabledesc), "table descriptors");
+    p.instrs.resize(p.h.n_instrs);
+    take(p.instrs.data(), p.h.n_instrs * sizeof(sigops_instr), "instructions");
+    p.pieces.resize(p.h.n_pieces);
+    take(p.pieces.data(), p.h.n_pieces * sizeof(sigops_piece), "pieces");
+    std::vector<sigops_stage> st(p.h.n_stages);
+    take(st.data(), p.h.n_stages * sizeof(sigops_stage), "stages");
+    p.blob.resize(p.h.n_table_doubles);
+    take(p.blob.data(), p.h.n_table_doubles * sizeof(double), "coefficient blob");
+    if (cur != end) fail(SIGOPS_ERR_INVALID, "%zu trailing bytes after the plan", (size_t)(end - cur));
+
+    for (auto& b : p.bufs) {
+        if (b.nframes < 0 || b.nchannels < 1 || b.nchannels > 65535) fail(SIGOPS_ERR_INVALID, "buffer with %lld frames x %d channels", (long long)b.nframes, b.nchannels);
+        if (b.dtype != SIGOPS_F32 && b.dtype != SIGOPS_F64 && b.dtype != SIGOPS_I64) fail(SIGOPS_ERR_INVALID, "unknown sample type %d", b.dtype);
+    }
+    for (auto& t : p.tables)
+        if (t.offset < 0 || t.count < 0 || (uint64_t)(t.offset + t.count) > p.h.n_table_doubles) fail(SIGOPS_ERR_INVALID, "table outside the blob");
+
+    p.stages.resize(st.size());
+    for (size_t i = 0; i < st.size(); ++i) {
+        StageRT& s = p.stages[i];
+        s.st = st[i];
+        const sigops_stage& g = s.st;
+        char what[64];
+        snprintf(what, sizeof what, "stage %zu", i);
+        if (g.out_buf < (int)p.h.n_inputs || g.out_buf >= p.nbuf()) fail(SIGOPS_ERR_INVALID, "%s: output buffer %d is not a temp/output", what, g.out_buf);
+        if (g.sumsq_slot >= (int)p.h.n_scalars) fail(SIGOPS_ERR_INVALID, "%s: scalar slot %d of %u", what, g.sumsq_slot, p.h.n_scalars);
+        const sigops_bufdesc& ob = p.bufs[g.out_buf];
+        if (g.kind == SIGOPS_STAGE_MAP) {
+            if (g.n_pieces < 1 || g.n_pieces > kMaxPieces) fail(SIGOPS_ERR_UNSUPPORTED, "%s: %d pieces (1..%d supported)", what, g.n_pieces, kMaxPieces);
+            if (g.piece_start < 0 || (size_t)g.piece_start + g.n_pieces > p.pieces.size()) fail(SIGOPS_ERR_INVALID, "%s: piece range", what);
+            for (int k = 0; k < g.n_pieces; ++k) {
+                const sigops_piece& pc = p.pieces[g.piece_start + k];
+                if (pc.out_start < 0 || pc.out_len < 0 || pc.out_start + pc.out_len > ob.nframes) fail(SIGOPS_ERR_INVALID, "%s: piece %d outside the output (%lld+%lld > %lld)", what, k, (long long)pc.out_start, (long long)pc.out_len, (long long)ob.nframes);
+                if (pc.ch_start < 0 || pc.ch_count < 1 || pc.ch_start + pc.ch_count > ob.nchannels) fail(SIGOPS_ERR_INVALID, "%s: piece %d channel range", what, k);
+                p.max_stack = std::max(p.max_stack, program_stack_depth(p, pc.prog_start, pc.prog_len, false, what));
+                if (pc.prog_len < 1) fail(SIGOPS_ERR_INVALID, "%s: empty program", what);
+            }
+        } else if (g.kind == SIGOPS_STAGE_IIR || g.kind == SIGOPS_STAGE_FIR) {
+            if (g.nchannels != ob.nchannels || g.n_out != ob.nframes) fail(SIGOPS_ERR_INVALID, "%s: stage shape %lldx%d != output buffer %lldx%d", what, (long long)g.n_out, g.nchannels, (long long)ob.nframes, ob.nchannels);
+            if (g.in_prog_len < 1) fail(SIGOPS_ERR_INVALID, "%s: missing input program", what);
+            p.max_stack = std::max(p.max_stack, program_stack_depth(p, g.in_prog_start, g.in_prog_len, false, what));
+            p.max_stack = std::max(p.max_stack, program_stack_depth(p, g.epi_prog_start, g.epi_prog_len, true, what));
+            if (g.kind == SIGOPS_STAGE_IIR) derive_iir(p, s, (int)i);
+            else derive_fir(p, s, (int)i);
+        } else
+            fail(SIGOPS_ERR_INVALID, "%s: unknown kind %d", what, g.kind);
+    }
+}
+
+// ---- device-side plan constants -------------------------------------------------
+
+void ensure_plan_dev(sigops_plan& p, int di) {
+    PlanDev& d = p.dev[di];
+    if (d.ready) return;
+    CUDA_OK(cudaSetDevice(p.ctx->devs[di].ordinal));
+    if (!p.instrs.empty()) {
+        CUDA_OK(cudaMalloc(&d.instrs, p.instrs.size() * sizeof(sigops_instr)));
+        CUDA_OK(cudaMemcpy(d.instrs, p.instrs.data(), p.instrs.size() * sizeof(sigops_instr), cudaMemcpyHostToDevice));
+    }
+    if (!p.blob.empty()) {
+        CUDA_OK(cudaMalloc(&d.blob, p.blob.size() * sizeof(double)));
+        CUDA_OK(cudaMemcpy(d.blob, p.blob.data(), p.blob.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    d.xi0.assign(p.stages.size(), nullptr);
+    d.phi.assign(p.stages.size(), nullptr);
+    for (size_t i = 0; i < p.stages.size(); ++i) {
+        const FirDerived& f = p.stages[i].fir;
+        if (p.stages[i].st.kind != SIGOPS_STAGE_FIR) continue;
+        CUDA_OK(cudaMalloc(&d.xi0[i], f.xi0.size() * sizeof(int64_t)));
+        CUDA_OK(cudaMalloc(&d.phi[i], f.phi.size() * sizeof(double)));
+        CUDA_OK(cudaMemcpy(d.xi0[i], f.xi0.data(), f.xi0.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(d.phi[i], f.phi.data(), f.phi.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    d.ready = true;
+}
+
+void free_plan_dev(sigops_plan& p) {
+    for (size_t di = 0; di < p.dev.size(); ++di) {
+        PlanDev& d = p.dev[di];
+        if (!d.ready) continue;
+        cudaSetDevice(p.ctx->devs[di].ordinal);
+        cudaFree(d.instrs);
+        cudaFree(d.blob);
+        for (auto q : d.xi0) cudaFree(q);
+        for (auto q : d.phi) cudaFree(q);
+        d.ready = false;
+    }
+}
+
+// ---- IIR chunking ---------------------------------------------------------------
+
+struct IirLaunch {
+    int blocks_per_row;
+    int64_t L, Wc, nchunks;
+    bool need_matrix;
+};
+
+IirLaunch choose_iir_chunking(const StageRT& s, int64_t rows, int sm_count) {
+    const int64_t N = s.st.n_out;
+    const int64_t W32 = round_up(std::max<int64_t>(s.iir.W, 1), 32);
+    const int64_t target_blocks = (int64_t)sm_count * 4;
+    int bpr = 1;
+    auto Lof = [&](int b) { return std::max<int64_t>(32, round_up((N + (int64_t)b * kIirThreads - 1) / ((int64_t)b * kIirThreads), 32)); };
+    const int64_t Lmin = std::max<int64_t>(256, std::min<int64_t>(4 * W32, 8192));
+    while (rows * bpr < target_blocks && Lof(bpr * 2) >= Lmin && bpr < 4096) bpr *= 2;
+    IirLaunch r;
+    r.blocks_per_row = bpr;
+    r.L = Lof(bpr);
+    r.nchunks = (N + r.L - 1) / r.L;
+    r.Wc = std::min(W32, r.L);
+    r.need_matrix = s.iir.W >= r.L;
+    return r;
+}
+
+// ---- one wave of instances on one device ------------------------------------------
+
+struct WaveIO {
+    int64_t ninst;
+    const sigops_buffer* in;   // device pointers, [ninst][n_inputs]
+    const sigops_buffer* out;  // [ninst][n_outputs]
+};
+
+size_t temp_bytes_per_instance(const sigops_plan& p) {
+    size_t total = 0;
+    for (uint32_t t = 0; t < p.h.n_temps; ++t) {
+        const sigops_bufdesc& b = p.bufs[p.h.n_inputs + t];
+        total += (size_t)round_up(round_up(std::max<int64_t>(b.nframes, 1), 16) * b.nchannels * (int64_t)elem_size(b.dtype), 256);
+    }
+    return total;
+}
+
+size_t iir_state_bytes(const sigops_plan& p, int64_t ninst, int sm_count) {
+    size_t total = 0;   // every IIR stage of a wave takes its own state arrays from the arena
+    for (auto& s : p.stages) {
+        if (s.st.kind != SIGOPS_STAGE_IIR) continue;
+        const int64_t rows = ninst * s.st.nchannels;
+        IirLaunch c = choose_iir_chunking(s, rows, sm_count);
+        total += (size_t)2 * (2 * s.iir.M) * rows * c.blocks_per_row * kIirThreads * sizeof(double) + 4096 + 1024;
+    }
+    return total;
+}
+
+size_t wave_workspace_bytes(const sigops_plan& p, int64_t ninst, int sm_count) {
+    return temp_bytes_per_instance(p) * ninst + iir_state_bytes(p, ninst, sm_count) +
+           (size_t)ninst * p.nbuf() * sizeof(BufRef) + (size_t)ninst * std::max<uint32_t>(p.h.n_scalars, 1) * sizeof(double) +
+           (1 << 16);
+}
+
+template <int MODE>
+void launch_iir(int M, dim3 grid, size_t smem, cudaStream_t st, const IirParams& P) {
+#define SIGOPS_IIR_CASE(m)                                                                                 \
+    case m:                                                                                                \
+        if (smem > 0) CUDA_OK(cudaFuncSetAttribute(k_iir<m, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_iir<m, MODE><<<grid, kIirThreads, smem, st>>>(P);                                                \
+        break;
+    switch (M) {
+        SIGOPS_IIR_CASE(1) SIGOPS_IIR_CASE(2) SIGOPS_IIR_CASE(3) SIGOPS_IIR_CASE(4)
+        SIGOPS_IIR_CASE(5) SIGOPS_IIR_CASE(6) SIGOPS_IIR_CASE(7) SIGOPS_IIR_CASE(8)
+        default: fail(SIGOPS_ERR_UNSUPPORTED, "IIR cascade of %d sections", M);
+    }
+#undef SIGOPS_IIR_CASE
+    CUDA_OK(cudaGetLastError());
+}
+
+// Enqueue every stage of the plan for one wave. Returns kernels launched.
+int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, const WaveIO& io) {
+    Device& dev = p.ctx->devs[di];
+    PlanDev& pd = p.dev[di];
+    const int nbuf = p.nbuf();
+    const int64_t ninst = io.ninst;
+    const int nscal = std::max<uint32_t>(p.h.n_scalars, 1);
+    int64_t launches = 0;
+
+    // -- workspace carve-up
+    const size_t temp_stride = temp_bytes_per_instance(p);
+    char* temps = temp_stride ? (char*)slot.arena.take(temp_stride * ninst) : nullptr;
+    double* scalars = (double*)slot.arena.take((size_t)ninst * nscal * sizeof(double));
+    BufRef* d_refs = (BufRef*)slot.arena.take((size_t)ninst * nbuf * sizeof(BufRef));
+    CUDA_OK(cudaMemsetAsync(scalars, 0, (size_t)ninst * nscal * sizeof(double), stream));
+
+    // -- BufRef table (instance-major)
+    const size_t table_bytes = (size_t)ninst * nbuf * sizeof(BufRef);
+    if (slot.pinned_cap < table_bytes) {
+        if (slot.pinned) cudaFreeHost(slot.pinned);
+        slot.pinned = nullptr;
+        CUDA_OK(cudaMallocHost(&slot.pinned, table_bytes));
+        slot.pinned_cap = table_bytes;
+    }
+    std::vector<char> table(table_bytes);
+    BufRef* refs = (BufRef*)table.data();
+    for (int64_t i = 0; i < ninst; ++i) {
+        size_t toff = 0;
+        for (int b = 0; b < nbuf; ++b) {
+            BufRef& r = refs[i * nbuf + b];
+            const sigops_bufdesc& bd = p.bufs[b];
+            memset(&r, 0, sizeof r);
+            if (b < (int)p.h.n_inputs) {
+                const sigops_buffer& ib = io.in[i * p.h.n_inputs + b];
+                r.ptr = ib.ptr; r.ld = ib.ld; r.dtype = ib.dtype; r.nch = ib.nchannels;
+            } else if (b < (int)(p.h.n_inputs + p.h.n_temps)) {
+                const int64_t ld = round_up(std::max<int64_t>(bd.nframes, 1), 16);
+                r.ptr = temps + (size_t)i * temp_stride + toff;
+                r.ld = ld; r.dtype = bd.dtype; r.nch = bd.nchannels;
+                toff += (size_t)round_up(ld * bd.nchannels * (int64_t)elem_size(bd.dtype), 256);
+            } else {
+                const sigops_buffer& ob = io.out[i * p.h.n_outputs + (b - p.h.n_inputs - p.h.n_temps)];
+                r.ptr = ob.ptr; r.ld = ob.ld; r.dtype = ob.dtype; r.nch = ob.nchannels;
+            }
+        }
+    }
+    if (slot.last_table_dev != (void*)d_refs || slot.last_table != table) {
+        // the pinned staging buffer may still be in flight from the previous wave of this slot
+        CUDA_OK(cudaStreamSynchronize(stream));
+        memcpy(slot.pinned, table.data(), table_bytes);
+        CUDA_OK(cudaMemcpyAsync(d_refs, slot.pinned, table_bytes, cudaMemcpyHostToDevice, stream));
+        slot.last_table.swap(table);
+        slot.last_table_dev = d_refs;
+    }
+
+    const size_t stack_map = p.max_stack ? (size_t)p.max_stack * kMapV * kMapThreads * sizeof(double) : 0;
+    const size_t stack_iir = p.max_stack ? (size_t)p.max_stack * kIirV * kIirThreads * sizeof(double) : 0;
+
+    for (size_t si = 0; si < p.stages.size(); ++si) {
+        const StageRT& s = p.stages[si];
+        const sigops_stage& g = s.st;
+        if (g.kind == SIGOPS_STAGE_MAP) {
+            MapParams P{};
+            P.instrs = pd.instrs; P.bufrefs = d_refs; P.scalars = scalars;
+            P.nbuf = nbuf; P.nscalars = nscal;
+            P.out_buf = g.out_buf; P.sumsq_slot = g.sumsq_slot; P.out_nch = p.bufs[g.out_buf].nchannels;
+            P.n_pieces = g.n_pieces;
+            int tiles = 0;
+            for (int k = 0; k < g.n_pieces; ++k) {
+                P.pieces[k] = p.pieces[g.piece_start + k];
+                P.tile_prefix[k] = tiles;
+                tiles += (int)((P.pieces[k].out_len + kMapTile - 1) / kMapTile);
+            }
+            P.tile_prefix[g.n_pieces] = tiles;
+            if (tiles == 0) continue;
+            if (stack_map > 16 * 1024) CUDA_OK(cudaFuncSetAttribute(k_map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stack_map));
+            for (int64_t i0 = 0; i0 < ninst; i0 += 65535) {
+                const int64_t ni = std::min<int64_t>(65535, ninst - i0);
+                MapParams Q = P;
+                Q.bufrefs = d_refs + i0 * nbuf;
+                Q.scalars = scalars + i0 * nscal;
+                dim3 grid(tiles, P.out_nch, (unsigned)ni);
+                k_map<<<grid, kMapThreads, stack_map, stream>>>(Q);
+                CUDA_OK(cudaGetLastError());
+                ++launches;
+            }
+        } else if (g.kind == SIGOPS_STAGE_IIR) {
+            if (g.n_out == 0) continue;
+            const int64_t rows = ninst * g.nchannels;
+            const IirLaunch c = choose_iir_chunking(s, rows, dev.sm_count);
+            IirParams P{};
+            P.instrs = pd.instrs; P.bufrefs = d_refs; P.scalars = scalars;
+            P.nbuf = nbuf; P.nscalars = nscal;
+            P.out_buf = g.out_buf; P.sumsq_slot = g.sumsq_slot;
+            P.in_prog_start = g.in_prog_start; P.in_prog_len = g.in_prog_len;
+            P.epi_prog_start = g.epi_prog_start; P.epi_prog_len = g.epi_prog_len;
+            P.plain_in_buf = s.iir.plain_in ? s.iir.plain_buf : -1;
+            P.plain_in_len = s.iir.plain_len;
+            P.nch = g.nchannels; P.blocks_per_row = c.blocks_per_row;
+            P.N = g.n_out; P.L = c.L; P.Wc = c.Wc;
+            P.slots_per_row = (int64_t)c.blocks_per_row * kIirThreads;
+            P.M = s.iir.M; P.gain = g.gain;
+            const double* t = p.blob.data() + p.tables[g.coef_table].offset;
+            for (int j = 0; j < s.iir.M; ++j)
+                for (int k = 0; k < 5; ++k) P.coef[j][k] = t[j * 5 + k];
+            const size_t nslots = (size_t)rows * P.slots_per_row;
+            const int S = 2 * s.iir.M;
+            P.state_zs = (double*)slot.arena.take(nslots * S * sizeof(double));
+            P.state_in = (double*)slot.arena.take(nslots * S * sizeof(double));
+            dim3 grid((unsigned)(rows * c.blocks_per_row));
+            launch_iir<IIR_MAIN>(s.iir.M, grid, stack_iir, stream, P);
+            ++launches;
+            if (c.nchunks > 1) {
+                CarryParams C{};
+                C.state_zs = P.state_zs; C.state_in = P.state_in;
+                C.nrows = rows; C.slots_per_row = P.slots_per_row; C.nchunks = c.nchunks; C.M2 = S;
+                C.AL = nullptr;
+                if (c.need_matrix) {
+                    double cc[kIirMaxSections][5];
+                    for (int j = 0; j < s.iir.M; ++j)
+                        for (int k = 0; k < 5; ++k) cc[j][k] = P.coef[j][k];
+                    std::vector<double> AL = transition_matrix(cc, s.iir.M, c.L);
+                    double* dAL = (double*)slot.arena.take(AL.size() * sizeof(double));
+                    CUDA_OK(cudaMemcpyAsync(dAL, AL.data(), AL.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+                    CUDA_OK(cudaStreamSynchronize(stream));   // AL is a host temporary
+                    C.AL = dAL;
+                }
+                k_iir_carry<<<(unsigned)((rows + 127) / 128), 128, 0, stream>>>(C);
+                CUDA_OK(cudaGetLastError());
+                launch_iir<IIR_FIX>(s.iir.M, grid, stack_iir, stream, P);
+                launches += 2;
+            }
+        } else {
+            if (g.n_out == 0) continue;
+            const int64_t rows = ninst * g.nchannels;
+            FirParams P{};
+            P.instrs = pd.instrs; P.bufrefs = d_refs; P.scalars = scalars;
+            P.nbuf = nbuf; P.nscalars = nscal;
+            P.out_buf = g.out_buf; P.sumsq_slot = g.sumsq_slot;
+            P.in_buf = s.fir.in_buf; P.in_len = s.fir.in_len;
+            P.epi_prog_start = g.epi_prog_start; P.epi_prog_len = g.epi_prog_len;
+            P.nch = g.nchannels; P.nrows = rows; P.n_out = g.n_out;
+            P.tapsper = g.taps_per_phase; P.dpad = s.fir.dpad; P.tpad = g.taps_per_phase + 2 * s.fir.dpad;
+            P.pmax = s.fir.pmax;
+            P.pfb = pd.blob + p.tables[g.pfb_table].offset;
+            P.dpfb = g.dpfb_table >= 0 ? pd.blob + p.tables[g.dpfb_table].offset : nullptr;
+            P.xi0 = pd.xi0[si]; P.phi = pd.phi[si];
+            const size_t smem = ((size_t)kFirT * P.tpad + (size_t)std::max(P.pmax, kFirT) * kFirRowPitch +
+                                 (size_t)p.max_stack * 2 * kFirThreads) * sizeof(double);
+            CUDA_OK(cudaFuncSetAttribute(k_fir, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int64_t tiles = (g.n_out + kFirT - 1) / kFirT;
+            const int64_t groups = (rows + kFirRB - 1) / kFirRB;
+            for (int64_t g0 = 0; g0 < groups; g0 += 65535) {
+                FirParams Q = P;
+                const int64_t ng = std::min<int64_t>(65535, groups - g0);
+                // shift the row window by whole instances is not possible in general; shift rows instead
+                Q.nrows = rows;
+                dim3 grid((unsigned)tiles, (unsigned)ng);
+                if (g0 != 0) fail(SIGOPS_ERR_UNSUPPORTED, "FIR stage over more than %d rows per wave", 65535 * kFirRB);
+                k_fir<<<grid, kFirThreads, smem, stream>>>(Q);
+                CUDA_OK(cudaGetLastError());
+                ++launches;
+            }
+        }
+    }
+    return launches;
+}
+
+void validate_io(const sigops_plan& p, int64_t ninst, const sigops_buffer* in, const sigops_buffer* out) {
+    if (ninst < 0) fail(SIGOPS_ERR_INVALID, "negative instance count");
+    if (ninst > 0 && ((p.h.n_inputs && !in) || !out)) fail(SIGOPS_ERR_INVALID, "null buffer array");
+    for (int64_t i = 0; i < ninst; ++i) {
+        for (uint32_t b = 0; b < p.h.n_inputs + p.h.n_outputs; ++b) {
+            const bool isin = b < p.h.n_inputs;
+            const sigops_buffer& ub = isin ? in[i * p.h.n_inputs + b] : out[i * p.h.n_outputs + (b - p.h.n_inputs)];
+            const sigops_bufdesc& bd = isin ? p.bufs[b] : p.bufs[p.h.n_temps + b];
+            if (ub.nframes != bd.nframes || ub.nchannels != bd.nchannels || ub.dtype != bd.dtype)
+                fail(SIGOPS_ERR_INVALID, "instance %lld %s %u: buffer is %lldx%d type %d, plan expects %lldx%d type %d",
+                     (long long)i, isin ? "input" : "output", isin ? b : b - p.h.n_inputs, (long long)ub.nframes, ub.nchannels,
+                     ub.dtype, (long long)bd.nframes, bd.nchannels, bd.dtype);
+            if (ub.ld < ub.nframes) fail(SIGOPS_ERR_INVALID, "instance %lld: ld %lld < nframes %lld", (long long)i, (long long)ub.ld, (long long)ub.nframes);
+            if (!ub.ptr && ub.nframes > 0) fail(SIGOPS_ERR_INVALID, "instance %lld: null buffer pointer", (long long)i);
+        }
+    }
+}
+
+int64_t count_out_samples(const sigops_plan& p, int64_t ninst) {
+    int64_t n = 0;
+    for (uint32_t b = 0; b < p.h.n_outputs; ++b) {
+        const sigops_bufdesc& bd = p.bufs[p.h.n_inputs + p.h.n_temps + b];
+        n += bd.nframes * bd.nchannels;
+    }
+    return n * ninst;
+}
+
+// Device-resident run: waves bounded by the workspace budget, all on `stream`.
+int64_t run_device_resident(sigops_plan& p, int di, int64_t ninst, const sigops_buffer* in,
+                            const sigops_buffer* out, cudaStream_t stream, Slot& slot) {
+    Device& dev = p.ctx->devs[di];
+    CUDA_OK(cudaSetDevice(dev.ordinal));
+    ensure_plan_dev(p, di);
+    if (ninst == 0) return 0;
+    int64_t wave = ninst;
+    while (wave > 1 && wave_workspace_bytes(p, wave, dev.sm_count) > p.ctx->ws_budget) wave = (wave + 1) / 2;
+    const size_t need = wave_workspace_bytes(p, wave, dev.sm_count);
+    if (need > slot.arena.cap) {
+        CUDA_OK(cudaStreamSynchronize(stream));
+        slot.arena.reserve(need);
+        slot.last_table_dev = nullptr;
+    }
+    int64_t launches = 0;
+    for (int64_t i0 = 0; i0 < ninst; i0 += wave) {
+        slot.arena.reset();
+        WaveIO io{std::min(wave, ninst - i0), in ? in + i0 * p.h.n_inputs : nullptr, out + i0 * p.h.n_outputs};
+        launches += enqueue_wave(p, di, slot, stream, io);
+    }
+    return launches;
+}
+
+// ---- host-buffer run: H2D -> stages -> D2H, two pipeline slots per device ----------
+
+struct HostRunResult {
+    int64_t launches = 0, h2d = 0, d2h = 0;
+    double gpu_ms = 0, h2d_ms = 0, d2h_ms = 0;
+    int code = 0;
+    std::string msg;
+};
+
+void run_host_on_device(sigops_plan& p, int di, int64_t i_begin, int64_t i_end, const sigops_buffer* in,
+                        sigops_buffer* out, HostRunResult& res) {
+    try {
+        Device& dev = p.ctx->devs[di];
+        CUDA_OK(cudaSetDevice(dev.ordinal));
+        ensure_plan_dev(p, di);
+        const int64_t ninst = i_end - i_begin;
+        if (ninst <= 0) return;
+        const uint32_t nin = p.h.n_inputs, nout = p.h.n_outputs;
+        // bytes of device staging one instance needs
+        size_t io_bytes = 0;
+        for (uint32_t b = 0; b < nin + nout; ++b) {
+            const sigops_bufdesc& bd = b < nin ? p.bufs[b] : p.bufs[p.h.n_temps + b];
+            io_bytes += (size_t)round_up(round_up(std::max<int64_t>(bd.nframes, 1), 16) * bd.nchannels * (int64_t)elem_size(bd.dtype), 256);
+        }
+        const size_t budget = p.ctx->ws_budget / 2;
+        int64_t wave = ninst;
+        auto need_for = [&](int64_t w) { return wave_workspace_bytes(p, w, dev.sm_count) + io_bytes * w + (size_t)w * (nin + nout) * sizeof(sigops_buffer); };
+        // at least 4 waves when the batch allows it, so copies overlap compute
+        if (ninst >= 8) wave = (ninst + 3) / 4;
+        while (wave > 1 && need_for(wave) > budget) wave = (wave + 1) / 2;
+        for (int s = 0; s < 2; ++s) {
+            Slot& slot = dev.slots[s];
+            if (need_for(wave) > slot.arena.cap) {
+                CUDA_OK(cudaStreamSynchronize(slot.stream));
+                slot.arena.reserve(need_for(wave));
+                slot.last_table_dev = nullptr;
+            }
+        }
+        std::vector<sigops_buffer> din, dout;
+        int k = 0;
+        for (int64_t i0 = 0; i0 < ninst; i0 += wave, ++k) {
+            Slot& slot = dev.slots[k & 1];
+            cudaStream_t st = slot.stream;
+            const int64_t w = std::min(wave, ninst - i0);
+            if (k >= 2) {   // the slot's previous wave must have drained before its arena is reused
+                CUDA_OK(cudaStreamSynchronize(st));
+                float ms = 0;
+                cudaEventElapsedTime(&ms, slot.ev[0], slot.ev[1]); res.h2d_ms += ms;
+                cudaEventElapsedTime(&ms, slot.ev[1], slot.ev[2]); res.gpu_ms += ms;
+                cudaEventElapsedTime(&ms, slot.ev[2], slot.ev[3]); res.d2h_ms += ms;
+            }
+            slot.arena.reset();
+            din.assign((size_t)w * nin, sigops_buffer{});
+            dout.assign((size_t)w * nout, sigops_buffer{});
+            CUDA_OK(cudaEventRecord(slot.ev[0], st));
+            for (int64_t i = 0; i < w; ++i) {
+                for (uint32_t b = 0; b < nin; ++b) {
+                    const sigops_buffer& hb = in[(i_begin + i0 + i) * nin + b];
+                    sigops_buffer& db = din[i * nin + b];
+                    db = hb;
+                    db.ld = round_up(std::max<int64_t>(hb.nframes, 1), 16);
+                    const size_t es = elem_size(hb.dtype);
+                    db.ptr = slot.arena.take((size_t)db.ld * hb.nchannels * es);
+                    if (hb.nframes > 0) {
+                        CUDA_OK(cudaMemcpy2DAsync(db.ptr, db.ld * es, hb.ptr, hb.ld * es, hb.nframes * es, hb.nchannels, cudaMemcpyHostToDevice, st));
+                        res.h2d += hb.nframes * hb.nchannels * (int64_t)es;
+                    }
+                }
+                for (uint32_t b = 0; b < nout; ++b) {
+                    const sigops_buffer& hb = out[(i_begin + i0 + i) * nout + b];
+                    sigops_buffer& db = dout[i * nout + b];
+                    db = hb;
+                    db.ld = round_up(std::max<int64_t>(hb.nframes, 1), 16);
+                    db.ptr = slot.arena.take((size_t)db.ld * hb.nchannels * elem_size(hb.dtype));
+                }
+            }
+            CUDA_OK(cudaEventRecord(slot.ev[1], st));
+            WaveIO io{w, din.data(), dout.data()};
+            res.launches += enqueue_wave(p, di, slot, st, io);
+            CUDA_OK(cudaEventRecord(slot.ev[2], st));
+            for (int64_t i = 0; i < w; ++i)
+                for (uint32_t b = 0; b < nout; ++b) {
+                    const sigops_buffer& hb = out[(i_begin + i0 + i) * nout + b];
+                    const sigops_buffer& db = dout[i * nout + b];
+                    const size_t es = elem_size(hb.dtype);
+                    if (hb.nframes > 0) {
+                        CUDA_OK(cudaMemcpy2DAsync(hb.ptr, hb.ld * es, db.ptr, db.ld * es, hb.nframes * es, hb.nchannels, cudaMemcpyDeviceToHost, st));
+                        res.d2h += hb.nframes * hb.nchannels * (int64_t)es;
+                    }
+                }
+            CUDA_OK(cudaEventRecord(slot.ev[3], st));
+        }
+        for (int s = 0; s < std::min(k, 2); ++s) {
+            Slot& slot = dev.slots[s];
+            CUDA_OK(cudaStreamSynchronize(slot.stream));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, slot.ev[0], slot.ev[1]); res.h2d_ms += ms;
+            cudaEventElapsedTime(&ms, slot.ev[1], slot.ev[2]); res.gpu_ms += ms;
+            cudaEventElapsedTime(&ms, slot.ev[2], slot.ev[3]); res.d2h_ms += ms;
+        }
+    } catch (const Failure& f) {
+        res.code = f.code;
+        res.msg = f.msg;
+        for (int s = 0; s < 2; ++s) cudaStreamSynchronize(p.ctx->devs[di].slots[s].stream);
+    }
+}
+
+// ---- micro-benchmarks for the roofline denominators ---------------------------------
+
+__global__ void k_dfma_peak(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+__global__ void k_copy_peak(const double2* __restrict__ src, double2* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+template <class F>
+int guarded(sigops_ctx* ctx, F&& f) {
+    try {
+        f();
+        return SIGOPS_OK;
+    } catch (const Failure& e) {
+        if (ctx) {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            ctx->err = e.msg;
+        } else
+            g_tls_error = e.msg;
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        if (ctx) ctx->err = "host allocation failed";
+        else g_tls_error = "host allocation failed";
+        return SIGOPS_ERR_NOMEM;
+    } catch (const std::exception& e) {
+        if (ctx) ctx->err = e.what();
+        else g_tls_error = e.what();
+        return SIGOPS_ERR_INVALID;
+    }
+}
+
+}  // namespace
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+
+extern "C" {
+
+int sigops_abi_version(void) { return SIGOPS_ABI_VERSION; }
+
+int sigops_device_count(int* count) {
+    return guarded(nullptr, [&] {
+        if (!count) fail(SIGOPS_ERR_INVALID, "null argument");
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            n = 0;
+        }
+        *count = n;
+    });
+}
+
+int sigops_ctx_create(const int* devices, int ndev, sigops_ctx** out) {
+    return guarded(nullptr, [&] {
+        if (!out) fail(SIGOPS_ERR_INVALID, "null argument");
+        *out = nullptr;
+        int have = 0;
+        cudaError_t e = cudaGetDeviceCount(&have);
+        if (e != cudaSuccess || have == 0) {
+            cudaGetLastError();
+            fail(SIGOPS_ERR_CUDA, "no CUDA device available (%s); the GPU sink has no CPU fallback",
+                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        }
+        std::vector<int> ords;
+        if (!devices || ndev <= 0) ords.push_back(0);
+        else ords.assign(devices, devices + ndev);
+        auto ctx = std::make_unique<sigops_ctx>();
+        for (int o : ords) {
+            if (o < 0 || o >= have) fail(SIGOPS_ERR_INVALID, "device ordinal %d of %d", o, have);
+            cudaDeviceProp prop;
+            CUDA_OK(cudaGetDeviceProperties(&prop, o));
+            if (prop.major < 10) fail(SIGOPS_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", o, prop.major, prop.minor);
+            Device d;
+            d.ordinal = o;
+            d.sm_count = prop.multiProcessorCount;
+            CUDA_OK(cudaSetDevice(o));
+            for (int s = 0; s < 2; ++s) {
+                CUDA_OK(cudaStreamCreateWithFlags(&d.slots[s].stream, cudaStreamNonBlocking));
+                for (auto& ev : d.slots[s].ev) CUDA_OK(cudaEventCreate(&ev));
+            }
+            ctx->devs.push_back(std::move(d));
+        }
+        if (const char* b = getenv("SIGOPS_WS_BYTES")) ctx->ws_budget = std::max<size_t>(size_t(64) << 20, strtoull(b, nullptr, 10));
+        *out = ctx.release();
+    });
+}
+
+void sigops_ctx_destroy(sigops_ctx* ctx) {
+    if (!ctx) return;
+    for (auto& d : ctx->devs) {
+        cudaSetDevice(d.ordinal);
+        for (auto& s : d.slots) {
+            if (s.stream) cudaStreamSynchronize(s.stream);
+            s.arena.release();
+            if (s.pinned) cudaFreeHost(s.pinned);
+            for (auto& ev : s.ev)
+                if (ev) cudaEventDestroy(ev);
+            if (s.stream) cudaStreamDestroy(s.stream);
+        }
+    }
+    delete ctx;
+}
+
+const char* sigops_last_error(sigops_ctx* ctx) {
+    if (!ctx) return g_tls_error.c_str();
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    g_tls_error = ctx->err;
+    return g_tls_error.c_str();
+}
+
+int sigops_plan_create(sigops_ctx* ctx, const void* plan, size_t nbytes, sigops_plan** out) {
+    return guarded(ctx, [&] {
+        if (!ctx || !plan || !out) fail(SIGOPS_ERR_INVALID, "null argument");
+        *out = nullptr;
+        auto p = std::make_unique<sigops_plan>();
+        p->ctx = ctx;
+        parse_plan(*p, plan, nbytes);
+        p->dev.resize(ctx->devs.size());
+        *out = p.release();
+    });
+}
+
+void sigops_plan_destroy(sigops_plan* plan) {
+    if (!plan) return;
+    free_plan_dev(*plan);
+    delete plan;
+}
+
+int sigops_plan_run_device(sigops_plan* plan, int dev_index, int64_t ninst, const sigops_buffer* in,
+                           sigops_buffer* out, void* cuda_stream, sigops_stats* stats) {
+    if (!plan) return SIGOPS_ERR_INVALID;
+    return guarded(plan->ctx, [&] {
+        sigops_ctx* ctx = plan->ctx;
+        if (dev_index < 0 || dev_index >= (int)ctx->devs.size()) fail(SIGOPS_ERR_INVALID, "device index %d of %zu", dev_index, ctx->devs.size());
+        validate_io(*plan, ninst, in, out);
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        Device& dev = ctx->devs[dev_index];
+        Slot& slot = dev.slots[0];
+        cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : slot.stream;
+        auto t0 = std::chrono::steady_clock::now();
+        CUDA_OK(cudaSetDevice(dev.ordinal));
+        if (stats) CUDA_OK(cudaEventRecord(slot.ev[4], st));
+        const int64_t launches = run_device_resident(*plan, dev_index, ninst, in, out, st, slot);
+        if (stats) CUDA_OK(cudaEventRecord(slot.ev[5], st));
+        if (!cuda_stream || stats) CUDA_OK(cudaStreamSynchronize(st));
+        if (stats) {
+            memset(stats, 0, sizeof *stats);
+            float ms = 0;
+            CUDA_OK(cudaEventElapsedTime(&ms, slot.ev[4], slot.ev[5]));
+            stats->gpu_ms = ms;
+            stats->launches = launches;
+            stats->out_samples = count_out_samples(*plan, ninst);
+            stats->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
+    });
+}
+
+int sigops_plan_run(sigops_plan* plan, int64_t ninst, const sigops_buffer* in, sigops_buffer* out,
+                    sigops_stats* stats) {
+    if (!plan) return SIGOPS_ERR_INVALID;
+    return guarded(plan->ctx, [&] {
+        sigops_ctx* ctx = plan->ctx;
+        validate_io(*plan, ninst, in, out);
+        std::unique_lock<std::mutex> lk(ctx->mu);
+        auto t0 = std::chrono::steady_clock::now();
+        const int nd = (int)ctx->devs.size();
+        std::vector<HostRunResult> res(nd);
+        std::vector<std::thread> th;
+        for (int d = 0; d < nd; ++d) {
+            const int64_t b = ninst * d / nd, e = ninst * (d + 1) / nd;
+            if (nd == 1) run_host_on_device(*plan, d, b, e, in, out, res[d]);
+            else th.emplace_back([&, d, b, e] { run_host_on_device(*plan, d, b, e, in, out, res[d]); });
+        }
+        for (auto& t : th) t.join();
+        lk.unlock();
+        for (auto& r : res)
+            if (r.code) throw Failure{r.code, r.msg};
+        if (stats) {
+            memset(stats, 0, sizeof *stats);
+            for (auto& r : res) {
+                stats->gpu_ms = std::max(stats->gpu_ms, r.gpu_ms);
+                stats->h2d_ms = std::max(stats->h2d_ms, r.h2d_ms);
+                stats->d2h_ms = std::max(stats->d2h_ms, r.d2h_ms);
+                stats->launches += r.launches;
+                stats->h2d_bytes += r.h2d;
+                stats->d2h_bytes += r.d2h;
+            }
+            stats->out_samples = count_out_samples(*plan, ninst);
+            stats->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
+    });
+}
+
+int sigops_plan_launch_count(sigops_plan* plan, int64_t* launches) {
+    if (!plan) return SIGOPS_ERR_INVALID;
+    return guarded(plan->ctx, [&] {
+        if (!launches) fail(SIGOPS_ERR_INVALID, "null argument");
+        int64_t n = 0;
+        for (auto& s : plan->stages) {
+            if (s.st.kind == SIGOPS_STAGE_IIR) n += s.st.n_out > 0 ? 3 : 0;   // upper bound: main + carry + fix
+            else n += 1;
+        }
+        *launches = n;
+    });
+}
+
+int sigops_plan_algorithmic_bytes(sigops_plan* plan, int64_t* bytes) {
+    if (!plan) return SIGOPS_ERR_INVALID;
+    return guarded(plan->ctx, [&] {
+        if (!bytes) fail(SIGOPS_ERR_INVALID, "null argument");
+        // every stage writes its output once and reads each distinct
+        // buffer it references once per output sample (generators/constants/ramps cost 0).
+        int64_t total = 0;
+        auto prog_reads = [&](int start, int len, int64_t frames, int nch) {
+            int64_t b = 0;
+            for (int i = 0; i < len; ++i) {
+                const sigops_instr& I = plan->instrs[start + i];
+                if (I.op > SIGOPS_OP_DIV) continue;
+                if (I.leaf == SIGOPS_LEAF_BUF) b += frames * nch * (int64_t)elem_size(plan->bufs[I.buf].dtype);
+                if (I.leaf == SIGOPS_LEAF_CHANSUM) b += frames * I.i2 * (int64_t)elem_size(plan->bufs[I.buf].dtype);
+            }
+            return b;
+        };
+        for (auto& s : plan->stages) {
+            const sigops_stage& g = s.st;
+            const sigops_bufdesc& ob = plan->bufs[g.out_buf];
+            if (g.kind == SIGOPS_STAGE_MAP) {
+                for (int k = 0; k < g.n_pieces; ++k) {
+                    const sigops_piece& pc = plan->pieces[g.piece_start + k];
+                    total += pc.out_len * pc.ch_count * (int64_t)elem_size(ob.dtype);
+                    total += prog_reads(pc.prog_start, pc.prog_len, pc.out_len, pc.ch_count);
+                }
+            } else {
+                total += g.n_out * g.nchannels * (int64_t)elem_size(ob.dtype);
+                total += prog_reads(g.in_prog_start, g.in_prog_len, g.n_in, g.nchannels);
+                total += prog_reads(g.epi_prog_start, g.epi_prog_len, g.n_out, g.nchannels);
+            }
+        }
+        *bytes = total;
+    });
+}
+
+int sigops_measure_peaks(sigops_ctx* ctx, int dev_index, double* dfma_per_s, double* copy_gbs) {
+    return guarded(ctx, [&] {
+        if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size()) fail(SIGOPS_ERR_INVALID, "bad device index");
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        Device& dev = ctx->devs[dev_index];
+        CUDA_OK(cudaSetDevice(dev.ordinal));
+        cudaStream_t st = dev.slots[0].stream;
+        cudaEvent_t e0 = dev.slots[0].ev[4], e1 = dev.slots[0].ev[5];
+        if (dfma_per_s) {
+            const int blocks = dev.sm_count * 8, threads = 256, iters = 1 << 14;
+            double* d = nullptr;
+            CUDA_OK(cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)));
+            double best = 0;
+            for (int rep = 0; rep < 5; ++rep) {
+                CUDA_OK(cudaEventRecord(e0, st));
+                k_dfma_peak<<<blocks, threads, 0, st>>>(d, iters, 0.999999, 1e-9);
+                CUDA_OK(cudaEventRecord(e1, st));
+                CUDA_OK(cudaStreamSynchronize(st));
+                float ms = 0;
+                CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+                best = std::max(best, (double)blocks * threads * iters * 8.0 / (ms * 1e-3));
+            }
+            cudaFree(d);
+            *dfma_per_s = best;
+        }
+        if (copy_gbs) {
+            const size_t n = size_t(1) << 26;   // 2 x 1 GiB
+            double2 *a = nullptr, *b = nullptr;
+            CUDA_OK(cudaMalloc(&a, n * sizeof(double2)));
+            CUDA_OK(cudaMalloc(&b, n * sizeof(double2)));
+            CUDA_OK(cudaMemsetAsync(a, 0, n * sizeof(double2), st));
+            double best = 0;
+            for (int rep = 0; rep < 6; ++rep) {
+                CUDA_OK(cudaEventRecord(e0, st));
+                k_copy_peak<<<dev.sm_count * 16, 512, 0, st>>>(a, b, n);
+                CUDA_OK(cudaEventRecord(e1, st));
+                CUDA_OK(cudaStreamSynchronize(st));
+                float ms = 0;
+                CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+                if (rep) best = std::max(best, 2.0 * n * sizeof(double2) / (ms * 1e-3) / 1e9);
+            }
+            cudaFree(a);
+            cudaFree(b);
+            *copy_gbs = best;
+        }
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+"""`sink(x, GPUSink())` — the drop-in for the reference's CPU `sink` (src/sink.jl).
+
+Follows the reference's custom-sink contract (docs/src/custom_sink.md:1-18) and
+the shape of its non-`Type` sink method `sink(x,to::String)` (src/sink.jl:139-142):
+`process_sink_params`, then hand the signal to the backend, then wrap the data
+like `initsink(x,T,data)` (src/sink.jl:120-121).  It never goes through
+`nextblock`/`frame`/`sink_helper!`: the graph is lowered once (lowering.py) and
+run by libsignalops_cuda.so.
+"""
+from __future__ import annotations
+
+import hashlib
+
+import numpy as np
+
+from . import cabi, graph as G
+from .lowering import Lowerer, np_dtype
+
+
+class Array:
+    """Sink-type token: return a bare array (Julia `Array`)."""
+
+
+class Tuple:
+    """Sink-type token: return `(array, framerate)` (Julia `Tuple`)."""
+
+
+class GPUSink:
+    """Materialise on B200s.  `devices`: CUDA ordinals to shard batches over."""
+
+    def __init__(self, devices=None, container=None):
+        self.devices = list(devices) if devices else [0]
+        self.container = container
+        self._ctx = None
+        self._plans = {}
+        self.last_stats = None
+
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            self._ctx = cabi.Context(self.devices)
+        return self._ctx
+
+    def compiled(self, plan_bytes):
+        key = hashlib.sha1(plan_bytes).digest()
+        cp = self._plans.get(key)
+        if cp is None:
+            cp = cabi.CompiledPlan(self.ctx, plan_bytes)
+            self._plans[key] = cp
+        return cp
+
+    def close(self):
+        for cp in self._plans.values():
+            cp.close()
+        self._plans.clear()
+        if self._ctx is not None:
+            self._ctx.close()
+            self._ctx = None
+
+
+def _wrap(plan, data, to):
+    container = to.container
+    if container is Array:
+        return data
+    if container is Tuple or plan.wants_tuple:
+        return data, plan.framerate
+    return data
+
+
+def _colmajor(a):
+    return a if a.ndim == 1 or a.shape[1] == 1 or a.flags.f_contiguous else np.asfortranarray(a)
+
+
+def sink(x=None, to=None):
+    """`sink(x, GPUSink())`; `sink(GPUSink())` curries like `sink(to)` at src/sink.jl:29.
+    A list/tuple of signals is a batch (one plan, many instances; additive API,
+    SURVEY.md §8b)."""
+    if isinstance(x, GPUSink) and to is None:
+        return lambda y: sink(y, x)
+    if not isinstance(to, GPUSink):
+        raise G.SignalError(
+            "this package only implements the GPU sink: call sink(x, GPUSink()). The CPU "
+            "`sink` belongs to the reference (restated under oracle/ for tests).")
+    if isinstance(x, list):
+        return sink_batch(x, to)
+    plan = Lowerer().build(x)
+    out = plan.outputs[0]
+    data = np.empty((out.nframes, out.nchannels), dtype=np_dtype(out.dtype), order="F")
+    if out.nframes > 0:
+        cp = to.compiled(plan.tobytes())
+        to.last_stats = cp.run_host(1, [_colmajor(a) for a in plan.input_arrays], [data])
+    return _wrap(plan, data, to)
+
+
+def sink_into(result, x, to):
+    """`sink!(result, x)` (src/sink.jl:158-168): write size(result,1) frames — a
+    prefix of `x` — into the caller's array, forcing the channel count."""
+    if isinstance(result, tuple):
+        return sink_into(result[0], x, to), result[1]
+    x = G.Signal(x)
+    n = result.shape[0]
+    nch = 1 if result.ndim == 1 else result.shape[1]
+    xn = x.nframes
+    if xn is not None and not G.isknowninf(xn) and xn < n:
+        raise G.SignalError(f"Signal is too short to fill buffer of length {n}.")
+    lw = Lowerer()
+    x = G.ToChannels(x, nch)
+    # the plan covers only the requested prefix, so infinite signals are fine here
+    plan = _build_prefix(lw, x, n, result.dtype)
+    if result.ndim == 2 and nch > 1 and not result.flags.f_contiguous:
+        tmp = np.empty(result.shape, dtype=result.dtype, order="F")
+        cp = to.compiled(plan.tobytes())
+        to.last_stats = cp.run_host(1, [_colmajor(a) for a in plan.input_arrays], [tmp])
+        result[...] = tmp
+    elif n > 0:
+        cp = to.compiled(plan.tobytes())
+        to.last_stats = cp.run_host(1, [_colmajor(a) for a in plan.input_arrays], [result])
+    return result
+
+
+def _build_prefix(lw, x, n, dtype):
+    from .lowering import STAGE_MAP, BufDesc, Stage, dtype_code
+    C = x.nchannels
+    lw.plan.outputs.append(BufDesc(n, C, dtype_code(dtype)))
+    lw.plan.framerate = x.framerate
+    pieces = lw.lower(x, 0, 0, n, 1, 0, 0, C) if n > 0 else []
+    lw.plan.stages.append(Stage(STAGE_MAP, ("out", 0), pieces=pieces, nchannels=C, n_out=n))
+    lw._fuse_epilogues()
+    lw._check_limits()
+    return lw.plan
+
+
+def sink_batch(xs, to):
+    """Materialise many structurally identical graphs in one call.  Every graph is
+    lowered; the plans must agree byte for byte (same operators, lengths and
+    constants) and differ only in the arrays they read."""
+    if not xs:
+        return []
+    plans = [Lowerer().build(x) for x in xs]
+    ref = plans[0].tobytes()
+    for k, p in enumerate(plans[1:], 1):
+        if p.tobytes() != ref:
+            raise G.SignalError(f"batch element {k} does not lower to the same plan as element 0")
+    out = plans[0].outputs[0]
+    datas = [np.empty((out.nframes, out.nchannels), dtype=np_dtype(out.dtype), order="F") for _ in xs]
+    if out.nframes > 0:
+        cp = to.compiled(ref)
+        ins = [_colmajor(a) for p in plans for a in p.input_arrays]
+        to.last_stats = cp.run_host(len(xs), ins, datas)
+    return [_wrap(plans[0], d, to) for d in datas]
