@@ -185,7 +185,7 @@ def _usepad(x, last_child_block):
             raise G.SignalError("Signal is length zero; there is no last frame to pad with.")
         n = last_child_block.n
         return frames_again_last(x.signal, last_child_block, n)
-    if p in (G.cycle, G.mirror):
+    if p is G.cycle or p is G.mirror:
         if not isinstance(x.signal, G.ArraySignal):
             raise G.SignalError("Attemped to specify an indexing pad function for a signal which is "
                                 "not known to support `getindex`.")
@@ -523,8 +523,7 @@ def sink_into(result, x, _force_channels=True):
     view = result.reshape(-1, 1) if result.ndim == 1 else result
     if _force_channels:
         x = G.ToChannels(x, view.shape[1])
-    if n > 0:
-        _sink_blocks(view, x, nextblock(x, n, False))
+    _sink_blocks(view, x, nextblock(x, n, False))     # called even when n == 0 (errors still fire)
     return result
 
 

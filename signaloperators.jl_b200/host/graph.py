@@ -350,8 +350,10 @@ def Signal(x=None, fs=None, **kwds):
     if callable(x):
         omega = kwds.pop("ω", kwds.pop("omega", None))
         omega = kwds.pop("frequency", omega)
-        phi = kwds.pop("ϕ", kwds.pop("phi", 0))
-        phi = kwds.pop("phase", phi)
+        phi = 0
+        for key in ("\u03d5", "\u03c6", "phi", "phase"):   # Python NFKC-normalises ϕ to φ in keywords
+            if key in kwds:
+                phi = kwds.pop(key)
         if kwds:
             raise TypeError(f"unexpected keyword arguments {list(kwds)}")
         try:

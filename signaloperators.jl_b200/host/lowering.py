@@ -277,11 +277,23 @@ class Lowerer:
         self.plan.wants_tuple = G.result_wants_tuple(x)
         out = ("out", 0)
         pieces = self.lower(x, 0, 0, N, 1, 0, 0, C) if N > 0 else []
+        if N == 0:
+            self._probe_cuts(x)
         st = Stage(STAGE_MAP, out, pieces=pieces, nchannels=C, n_out=N)
         self.plan.stages.append(st)
         self._fuse_epilogues()
         self._check_limits()
         return self.plan
+
+    def _probe_cuts(self, x):
+        """The reference calls `nextblock(x,0,false)` even for an empty result, so an
+        `After` that skips past the end of its child still throws (cutting.jl:174-181)."""
+        while isinstance(x, G.WrappedSignal):
+            if isinstance(x, G.CutApply) and x.kind == "after":
+                cn, k = x.signal.nframes, x.resolvelen()
+                if k is not None and cn is not None and not G.isknowninf(cn) and cn < k:
+                    raise G.SignalError(f"Signal is too short to skip {x.time}")
+            x = x.child()
 
     # ---- recursive lowering -------------------------------------------------------
     # Produce programs for consumer frames n in [lo,hi) and consumer channels
@@ -391,7 +403,7 @@ class Lowerer:
         b = nc - shift                       # first padded consumer frame
         p = x.pad
         T = x.sampletype
-        if p in (G.cycle, G.mirror, G.lastframe):
+        if any(p is q for q in (G.cycle, G.mirror, G.lastframe)):
             if p is not G.lastframe and not isinstance(child, G.ArraySignal):
                 raise G.SignalError("Attemped to specify an indexing pad function for a signal "
                                     "which is not known to support `getindex`.")     # padding.jl:172-181

@@ -22,7 +22,7 @@ __all__ = ["Hz", "kHz", "s", "ms", "frames", "kframes", "dB", "deg", "rad",
 class Quantity:
     """A number tagged with a dimension; `kind` in time/freq/frames/gain/angle."""
     __slots__ = ("value", "kind", "label")
-    __array_priority__ = 1000
+    __array_ufunc__ = None
 
     def __init__(self, value, kind, label=""):
         self.value = value
@@ -64,6 +64,8 @@ class Quantity:
 class Unit:
     """`5*s`, `s*5`, `10*ms` ... build quantities. Integer values convert
     through exact rationals (as Unitful does) so `10*ms` is the double nearest 1/100."""
+
+    __array_ufunc__ = None      # make numpy scalars defer to __rmul__ (keeps Float32 gains Float32)
 
     def __init__(self, kind, scale, label):
         self.kind = kind
