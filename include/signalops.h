@@ -105,6 +105,14 @@ int sigops_plan_run_device(sigops_plan* plan, int dev_index, int64_t ninst,
 int sigops_plan_launch_count(sigops_plan* plan, int64_t* launches);
 int sigops_plan_algorithmic_bytes(sigops_plan* plan, int64_t* bytes_per_instance);
 
+/* Per-launch timing for the roofline report: when enabled every kernel launch is
+ * bracketed by CUDA events on its own stream.  collect() synchronises the device
+ * and sums elapsed ms / launch counts by kernel kind
+ * (0 map, 1 iir main, 2 iir carry, 3 iir fix, 4 fir), then clears the record. */
+#define SIGOPS_KERNEL_KINDS 5
+int sigops_ctx_set_profiling(sigops_ctx* ctx, int enabled);
+int sigops_profile_collect(sigops_ctx* ctx, int dev_index, double* ms_by_kind, int64_t* count_by_kind, int nkinds);
+
 /* Measured FP64 FMA and HBM copy peaks of ctx device `dev_index` (micro-benchmarks
  * used for the roofline denominators; SURVEY.md §6 asks for the FP64 one). */
 int sigops_measure_peaks(sigops_ctx* ctx, int dev_index, double* dfma_per_s, double* copy_gbs);

@@ -31,10 +31,8 @@ namespace sigops {
 constexpr int kFirWarps = 8;
 constexpr int kFirThreads = kFirWarps * 32;
 constexpr int kFirR = 8;                    // outputs per thread
-constexpr int kFirG = 4;                    // rows per thread
 constexpr int kFirT = kFirWarps * kFirR;    // outputs per tile (64)
-constexpr int kFirRB = 32 * kFirG;          // rows per block (128)
-constexpr int kFirRowPitch = kFirRB + 1;
+// rows per thread G in {1,2,4}: rows per block RB = 32*G, smem row pitch RB+1
 
 struct FirParams {
     const sigops_instr* instrs;
@@ -56,8 +54,11 @@ struct FirParams {
     const double* phi;
 };
 
+template <int kFirG>
 __global__ void __launch_bounds__(kFirThreads)
 k_fir(const __grid_constant__ FirParams P) {
+    constexpr int kFirRB = 32 * kFirG;
+    constexpr int kFirRowPitch = kFirRB + 1;
     __shared__ sigops_instr sprog_epi[SIGOPS_MAX_PROG];
     __shared__ double lc_epi[kFirWarps][SIGOPS_MAX_PROG];
     __shared__ int64_t s_xi0[kFirT];

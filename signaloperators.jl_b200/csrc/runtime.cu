@@ -95,6 +95,36 @@ struct Slot {
     std::vector<char> last_table; // contents last uploaded (skip identical re-uploads)
     void* last_table_dev = nullptr;
     cudaEvent_t ev[6] = {};
+    // per-launch timing (sigops_ctx_set_profiling): (start, stop, kernel kind)
+    std::vector<cudaEvent_t> prof_pool;
+    std::vector<int> prof_kind;
+    size_t prof_used = 0;
+};
+
+enum { KIND_MAP = 0, KIND_IIR_MAIN, KIND_IIR_CARRY, KIND_IIR_FIX, KIND_FIR, KIND_COUNT };
+
+struct ProfScope {          // brackets one kernel launch with events when profiling is on
+    Slot* slot = nullptr;
+    cudaStream_t st = nullptr;
+    ProfScope(Slot& s, bool on, cudaStream_t stream, int kind) {
+        if (!on) return;
+        slot = &s;
+        st = stream;
+        if (s.prof_used + 2 > s.prof_pool.size()) {
+            for (int i = 0; i < 2; ++i) {
+                cudaEvent_t e;
+                CUDA_OK(cudaEventCreate(&e));
+                s.prof_pool.push_back(e);
+            }
+        }
+        s.prof_kind.push_back(kind);
+        CUDA_OK(cudaEventRecord(s.prof_pool[s.prof_used], st));
+    }
+    ~ProfScope() {
+        if (!slot) return;
+        cudaEventRecord(slot->prof_pool[slot->prof_used + 1], st);
+        slot->prof_used += 2;
+    }
 };
 
 struct Device {
@@ -142,6 +172,7 @@ struct sigops_ctx {
     std::string err;
     std::mutex mu;
     size_t ws_budget = size_t(16) << 30;
+    bool profiling = false;
 };
 
 struct sigops_plan {
@@ -290,6 +321,16 @@ void derive_iir(sigops_plan& p, StageRT& s, int idx) {
     }
 }
 
+constexpr size_t kFirSmemLimit = 200 * 1024;
+
+// dynamic shared memory of k_fir<G>: merged taps + transposed window (reused for the
+// output tile) + the interpreter's spill stack
+size_t fir_smem_bytes(const FirDerived& f, int tapsper, int G, int max_stack) {
+    const size_t pitch = 32 * G + 1;
+    return ((size_t)kFirT * (tapsper + 2 * f.dpad) + (size_t)std::max(f.pmax, kFirT) * pitch +
+            (size_t)max_stack * 2 * kFirThreads) * sizeof(double);
+}
+
 void derive_fir(sigops_plan& p, StageRT& s, int idx) {
     const sigops_stage& st = s.st;
     char what[64];
@@ -364,12 +405,9 @@ void derive_fir(sigops_plan& p, StageRT& s, int idx) {
     for (int64_t m = 0; m < padded; m += kFirT) span = std::max(span, s.fir.xi0[m + kFirT - 1] - s.fir.xi0[m]);
     s.fir.dpad = (int)dpad;
     s.fir.pmax = (int)(span + st.taps_per_phase);
-    const size_t smem = ((size_t)kFirT * (st.taps_per_phase + 2 * dpad) +
-                         (size_t)std::max<int64_t>(s.fir.pmax, kFirT) * kFirRowPitch +
-                         (size_t)SIGOPS_MAX_STACK * 2 * kFirThreads) * sizeof(double);
-    if (smem > 220 * 1024)
+    if (fir_smem_bytes(s.fir, st.taps_per_phase, 1, SIGOPS_MAX_STACK) > kFirSmemLimit)
         fail(SIGOPS_ERR_UNSUPPORTED, "%s: resampling ratio %g with %d taps/phase needs %zu bytes of shared memory per block",
-             what, st.rate, st.taps_per_phase, smem);
+             what, st.rate, st.taps_per_phase, fir_smem_bytes(s.fir, st.taps_per_phase, 1, SIGOPS_MAX_STACK));
 }
 
 void parse_plan(sigops_plan& p, const void* bytes, size_t nbytes) {
@@ -640,6 +678,7 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                 Q.bufrefs = d_refs + i0 * nbuf;
                 Q.scalars = scalars + i0 * nscal;
                 dim3 grid(tiles, P.out_nch, (unsigned)ni);
+                ProfScope ps(slot, p.ctx->profiling, stream, KIND_MAP);
                 k_map<<<grid, kMapThreads, stack_map, stream>>>(Q);
                 CUDA_OK(cudaGetLastError());
                 ++launches;
@@ -668,7 +707,10 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
             P.state_zs = (double*)slot.arena.take(nslots * S * sizeof(double));
             P.state_in = (double*)slot.arena.take(nslots * S * sizeof(double));
             dim3 grid((unsigned)(rows * c.blocks_per_row));
-            launch_iir<IIR_MAIN>(s.iir.M, grid, stack_iir, stream, P);
+            {
+                ProfScope ps(slot, p.ctx->profiling, stream, KIND_IIR_MAIN);
+                launch_iir<IIR_MAIN>(s.iir.M, grid, stack_iir, stream, P);
+            }
             ++launches;
             if (c.nchunks > 1) {
                 CarryParams C{};
@@ -685,9 +727,15 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                     CUDA_OK(cudaStreamSynchronize(stream));   // AL is a host temporary
                     C.AL = dAL;
                 }
-                k_iir_carry<<<(unsigned)((rows + 127) / 128), 128, 0, stream>>>(C);
+                {
+                    ProfScope ps(slot, p.ctx->profiling, stream, KIND_IIR_CARRY);
+                    k_iir_carry<<<(unsigned)((rows + 127) / 128), 128, 0, stream>>>(C);
+                }
                 CUDA_OK(cudaGetLastError());
-                launch_iir<IIR_FIX>(s.iir.M, grid, stack_iir, stream, P);
+                {
+                    ProfScope ps(slot, p.ctx->profiling, stream, KIND_IIR_FIX);
+                    launch_iir<IIR_FIX>(s.iir.M, grid, stack_iir, stream, P);
+                }
                 launches += 2;
             }
         } else {
@@ -705,22 +753,27 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
             P.pfb = pd.blob + p.tables[g.pfb_table].offset;
             P.dpfb = g.dpfb_table >= 0 ? pd.blob + p.tables[g.dpfb_table].offset : nullptr;
             P.xi0 = pd.xi0[si]; P.phi = pd.phi[si];
-            const size_t smem = ((size_t)kFirT * P.tpad + (size_t)std::max(P.pmax, kFirT) * kFirRowPitch +
-                                 (size_t)p.max_stack * 2 * kFirThreads) * sizeof(double);
-            CUDA_OK(cudaFuncSetAttribute(k_fir, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // rows per thread: as many as fit in shared memory, but no more than the batch can fill
+            int G = 4;
+            while (G > 1 && (fir_smem_bytes(s.fir, g.taps_per_phase, G, p.max_stack) > kFirSmemLimit || rows <= 16 * G)) G >>= 1;
+            const size_t smem = fir_smem_bytes(s.fir, g.taps_per_phase, G, p.max_stack);
             const int64_t tiles = (g.n_out + kFirT - 1) / kFirT;
-            const int64_t groups = (rows + kFirRB - 1) / kFirRB;
-            for (int64_t g0 = 0; g0 < groups; g0 += 65535) {
-                FirParams Q = P;
-                const int64_t ng = std::min<int64_t>(65535, groups - g0);
-                // shift the row window by whole instances is not possible in general; shift rows instead
-                Q.nrows = rows;
-                dim3 grid((unsigned)tiles, (unsigned)ng);
-                if (g0 != 0) fail(SIGOPS_ERR_UNSUPPORTED, "FIR stage over more than %d rows per wave", 65535 * kFirRB);
-                k_fir<<<grid, kFirThreads, smem, stream>>>(Q);
-                CUDA_OK(cudaGetLastError());
-                ++launches;
+            const int64_t groups = (rows + 32 * G - 1) / (32 * G);
+            if (groups > 65535) fail(SIGOPS_ERR_UNSUPPORTED, "FIR stage over more than %d rows per wave", 65535 * 32 * G);
+            dim3 grid((unsigned)tiles, (unsigned)groups);
+            ProfScope ps(slot, p.ctx->profiling, stream, KIND_FIR);
+            if (G == 4) {
+                CUDA_OK(cudaFuncSetAttribute(k_fir<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_fir<4><<<grid, kFirThreads, smem, stream>>>(P);
+            } else if (G == 2) {
+                CUDA_OK(cudaFuncSetAttribute(k_fir<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_fir<2><<<grid, kFirThreads, smem, stream>>>(P);
+            } else {
+                CUDA_OK(cudaFuncSetAttribute(k_fir<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_fir<1><<<grid, kFirThreads, smem, stream>>>(P);
             }
+            CUDA_OK(cudaGetLastError());
+            ++launches;
         }
     }
     return launches;
@@ -990,6 +1043,7 @@ void sigops_ctx_destroy(sigops_ctx* ctx) {
             if (s.pinned) cudaFreeHost(s.pinned);
             for (auto& ev : s.ev)
                 if (ev) cudaEventDestroy(ev);
+            for (auto& ev : s.prof_pool) cudaEventDestroy(ev);
             if (s.stream) cudaStreamDestroy(s.stream);
         }
     }
@@ -1132,6 +1186,41 @@ int sigops_plan_algorithmic_bytes(sigops_plan* plan, int64_t* bytes) {
             }
         }
         *bytes = total;
+    });
+}
+
+int sigops_ctx_set_profiling(sigops_ctx* ctx, int enabled) {
+    return guarded(ctx, [&] {
+        if (!ctx) fail(SIGOPS_ERR_INVALID, "null argument");
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->profiling = enabled != 0;
+        for (auto& d : ctx->devs)
+            for (auto& s : d.slots) {
+                s.prof_used = 0;
+                s.prof_kind.clear();
+            }
+    });
+}
+
+int sigops_profile_collect(sigops_ctx* ctx, int dev_index, double* ms_by_kind, int64_t* count_by_kind, int nkinds) {
+    return guarded(ctx, [&] {
+        if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size() || !ms_by_kind || !count_by_kind)
+            fail(SIGOPS_ERR_INVALID, "bad argument");
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        for (int k = 0; k < nkinds; ++k) { ms_by_kind[k] = 0; count_by_kind[k] = 0; }
+        Device& dev = ctx->devs[dev_index];
+        CUDA_OK(cudaSetDevice(dev.ordinal));
+        CUDA_OK(cudaDeviceSynchronize());
+        for (auto& s : dev.slots) {
+            for (size_t i = 0; i < s.prof_kind.size(); ++i) {
+                float ms = 0;
+                CUDA_OK(cudaEventElapsedTime(&ms, s.prof_pool[2 * i], s.prof_pool[2 * i + 1]));
+                const int k = s.prof_kind[i];
+                if (k < nkinds) { ms_by_kind[k] += ms; count_by_kind[k] += 1; }
+            }
+            s.prof_used = 0;
+            s.prof_kind.clear();
+        }
     });
 }
 

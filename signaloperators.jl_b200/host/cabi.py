@@ -16,7 +16,8 @@ F32, F64, I64 = 1, 2, 3
 SYMBOLS = ["sigops_abi_version", "sigops_device_count", "sigops_ctx_create", "sigops_ctx_destroy",
            "sigops_last_error", "sigops_plan_create", "sigops_plan_destroy", "sigops_plan_run",
            "sigops_plan_run_device", "sigops_plan_launch_count", "sigops_plan_algorithmic_bytes",
-           "sigops_measure_peaks"]
+           "sigops_measure_peaks", "sigops_ctx_set_profiling", "sigops_profile_collect"]
+KERNEL_KINDS = ["map", "iir_main", "iir_carry", "iir_fix", "fir"]
 
 
 class Buffer(C.Structure):
@@ -70,6 +71,8 @@ def load():
     lib.sigops_plan_launch_count.argtypes = [vp, C.POINTER(i64)]
     lib.sigops_plan_algorithmic_bytes.argtypes = [vp, C.POINTER(i64)]
     lib.sigops_measure_peaks.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.sigops_ctx_set_profiling.argtypes = [vp, C.c_int]
+    lib.sigops_profile_collect.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64), C.c_int]
     if lib.sigops_abi_version() != ABI_VERSION:
         raise RuntimeError("libsignalops_cuda.so ABI version mismatch")
     _lib = lib
@@ -106,6 +109,17 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def set_profiling(self, on):
+        _check(self.lib, self.handle, self.lib.sigops_ctx_set_profiling(self.handle, 1 if on else 0))
+
+    def profile_collect(self, dev_index=0):
+        """{kind: (total_ms, launches)} since profiling was enabled / last collected."""
+        n = len(KERNEL_KINDS)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        _check(self.lib, self.handle, self.lib.sigops_profile_collect(self.handle, dev_index, ms, cnt, n))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(KERNEL_KINDS) if cnt[i]}
 
     def measure_peaks(self, dev_index=0):
         a, b = C.c_double(), C.c_double()
