@@ -53,6 +53,11 @@ struct IirParams {
     int M;
     double gain;
     double coef[kIirMaxSections][5];
+    // FAST path: Float64 plain input buffer, Float64 output, epilogue = up to two
+    // constant multipliers applied in order (Amplify chains)
+    int n_epi_scale;
+    double epi_scale[2];
+    int carry_is_shift;        // FIX reads s_in[k] = state_zs[k-1] directly (no CARRY launch)
 };
 
 enum { IIR_MAIN = 0, IIR_FIX = 1 };
@@ -97,6 +102,191 @@ struct Cascade {
     }
 };
 
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src, bool valid) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int src_size = valid ? 8 : 0;       // src_size 0 => the 8 bytes are zero-filled, nothing is read
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(gmem_src), "r"(src_size) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// One section update (DSP.jl `_filt!` inner body).  UNITB: the
+// section has b0 == 1 and b2 == 1 exactly (every zero on the unit circle, which is
+// what the Butterworth/Chebyshev designs give), so `b0*x` and `b2*x` are skipped
+// without changing a single bit of the result.
+template <int M, bool UNITB>
+__device__ __forceinline__ double biquad_step(Cascade<M>& f, int j, double xi) {
+    double y;
+    if (UNITB) {
+        y = xi + f.s1[j];
+        f.s1[j] = fma(-f.a1[j], y, fma(f.b1[j], xi, f.s2[j]));
+        f.s2[j] = fma(-f.a2[j], y, xi);
+    } else {
+        y = fma(f.b0[j], xi, f.s1[j]);
+        f.s1[j] = fma(-f.a1[j], y, fma(f.b1[j], xi, f.s2[j]));
+        f.s2[j] = fma(-f.a2[j], y, f.b2[j] * xi);
+    }
+    return y;
+}
+
+// NT frames of one chunk through the cascade, software-pipelined across sections:
+// at step t section j works on frame t-j, so the M updates of a step are mutually
+// independent (M-way ILP on the FP64 pipe) while every frame still sees exactly the
+// sequential recurrence.  ZERO_IN: the first section's input is 0 (FIX pass).
+// out = in_tile + (cascade * gain) for FIX, (cascade * gain) * sc for MAIN.
+template <int M, int NT, bool ZERO_IN, bool UNITB>
+__device__ __forceinline__ void cascade_tile(Cascade<M>& f, double* myrow, double gain, double sc) {
+    // pull the lane's NT frames into registers first: the shared-memory latency is paid
+    // once per tile instead of once per frame on the critical path
+    double xr[NT];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) xr[k] = myrow[k];
+    double pipe[M];
+#pragma unroll
+    for (int t = 0; t < NT + M - 1; ++t) {
+#pragma unroll
+        for (int j = M - 1; j >= 0; --j) {     // descending: section j reads pipe[j-1] of step t-1
+            const int k = t - j;
+            if (k >= 0 && k < NT) {
+                const double in = (j == 0) ? (ZERO_IN ? 0.0 : xr[k]) : pipe[j - 1];
+                pipe[j] = biquad_step<M, UNITB>(f, j, in);
+                if (j == M - 1) myrow[k] = ZERO_IN ? fma(pipe[j], gain, xr[k]) * sc : (pipe[j] * gain) * sc;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kHalfCols = 16;          // frames per half-tile
+constexpr int kHalfPitch = 17;         // doubles; odd pitch keeps lane=row accesses conflict-free
+constexpr int kHalfElems = 32 * kHalfPitch;
+
+// FAST kernel: same decomposition as k_iir below, specialised for the common case
+// (Float64 buffer in, Float64 buffer out, constant-gain epilogue): no interpreter.
+// Each warp streams its 32 chunks through two 32x16 shared-memory half-tiles:
+// while it runs the cascade on one, cp.async is already filling the other, so every
+// warp always has 4 KB of reads in flight (global rows are 128-byte segments).
+template <int M, int MODE, bool UNITB>
+__global__ void __launch_bounds__(kIirThreads, 5)
+k_iir_fast(const __grid_constant__ IirParams P) {
+    __shared__ double tiles[kIirWarps][2][kHalfElems];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = blockIdx.x / P.blocks_per_row;
+    const int brow = blockIdx.x % P.blocks_per_row;
+    const int inst = (int)(row / P.nch), c = (int)(row % P.nch);
+    const BufRef ib = P.bufrefs[(size_t)inst * P.nbuf + P.plain_in_buf];
+    const BufRef ob = P.bufrefs[(size_t)inst * P.nbuf + P.out_buf];
+    const double* __restrict__ xin = reinterpret_cast<const double*>(ib.ptr) + (int64_t)c * ib.ld;
+    double* yout = reinterpret_cast<double*>(ob.ptr) + (int64_t)c * ob.ld;
+    const int64_t nvalid = P.plain_in_len < P.N ? P.plain_in_len : P.N;
+
+    const int64_t chunk0 = (int64_t)brow * kIirThreads + warp * 32;
+    const int64_t mychunk = chunk0 + lane;
+    const int64_t slot = row * P.slots_per_row + mychunk;
+    const int64_t nslots = (int64_t)gridDim.x / P.blocks_per_row * P.slots_per_row;
+    if (chunk0 * P.L >= P.N) return;
+    // every frame of the warp's 32 chunks exists in both buffers: no bounds checks needed
+    const bool interior = (chunk0 + 32) * P.L <= nvalid;
+
+    Cascade<M> f;
+    f.init(P);
+    if (MODE == IIR_FIX && mychunk >= 1) {
+        const double* sin_ = P.carry_is_shift ? P.state_zs : P.state_in;
+        const int64_t src = P.carry_is_shift ? slot - 1 : slot;
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            f.s1[j] = sin_[(2 * j) * nslots + src];
+            f.s2[j] = sin_[(2 * j + 1) * nslots + src];
+        }
+    }
+    const int64_t L = P.L;
+    const int64_t nh_raw = P.Wc / kHalfCols;
+    const int64_t nh = (MODE == IIR_FIX) ? nh_raw : L / kHalfCols;
+    const double sc_final = P.epi_scale[0] * P.epi_scale[1];
+    // copy mapping: instruction i moves rows 2i and 2i+1; lanes 0-15 / 16-31 take one row each
+    const int crow = lane >> 4, ccol = lane & 15;
+    const int64_t cbase = (chunk0 + crow) * L + ccol;      // frame of (row crow, col ccol) in half-tile 0
+    double ss = 0.0;
+
+    auto issue_loads = [&](int64_t h, double* buf) {
+        const double* gsrc = (MODE == IIR_MAIN) ? xin : yout;
+        const int64_t n0 = cbase + h * kHalfCols;
+        double* dst = buf + crow * kHalfPitch + ccol;
+        if (interior && (MODE == IIR_MAIN || chunk0 >= 1)) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cp_async8(dst + 2 * i * kHalfPitch, gsrc + n0 + 2 * i * L, true);
+        } else {
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int64_t n = n0 + 2 * i * L;
+                const bool ok = (MODE == IIR_MAIN) ? (n < nvalid) : (n < P.N && chunk0 + 2 * i + crow >= 1);
+                cp_async8(dst + 2 * i * kHalfPitch, gsrc + (ok ? n : 0), ok);
+            }
+        }
+        cp_async_commit();
+    };
+
+    issue_loads(0, tiles[warp][0]);
+    for (int64_t h = 0; h < nh; ++h) {
+        double* buf = tiles[warp][h & 1];
+        if (h + 1 < nh) {
+            issue_loads(h + 1, tiles[warp][(h + 1) & 1]);
+            cp_async_wait_group<1>();
+        } else {
+            cp_async_wait_group<0>();
+        }
+        __syncwarp();
+        // MAIN leaves the first Wc frames of chunks >= 1 un-scaled (raw zero-state
+        // response): FIX adds the carried-in state's response and applies the gain.
+        const bool raw_phase = (MODE == IIR_MAIN) && (h < nh_raw);
+        const double sc = (raw_phase && mychunk >= 1) ? 1.0 : sc_final;
+        cascade_tile<M, kHalfCols, MODE == IIR_FIX, UNITB>(f, buf + lane * kHalfPitch, P.gain, sc);
+        __syncwarp();
+        // ---- store: rows as 128-byte segments
+        const int64_t n0 = cbase + h * kHalfCols;
+        const double* srcs = buf + crow * kHalfPitch + ccol;
+        if (interior && chunk0 >= 1) {
+            double v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = srcs[2 * i * kHalfPitch];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                yout[n0 + 2 * i * L] = v[i];
+                if (!raw_phase) ss = fma(v[i], v[i], ss);
+            }
+        } else {
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int64_t n = n0 + 2 * i * L;
+                const int64_t chunk = chunk0 + 2 * i + crow;
+                const double w = srcs[2 * i * kHalfPitch];
+                const bool skip = (MODE == IIR_FIX) && chunk < 1;
+                if (n < P.N && !skip) {
+                    yout[n] = w;
+                    if (!(raw_phase && chunk >= 1)) ss = fma(w, w, ss);
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    if (MODE == IIR_MAIN) {
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            P.state_zs[(2 * j) * nslots + slot] = f.s1[j];
+            P.state_zs[(2 * j + 1) * nslots + slot] = f.s2[j];
+        }
+    }
+    if (P.sumsq_slot >= 0) {
+        ss = warp_sum(ss);
+        if (lane == 0) atomicAdd(P.scalars + (size_t)inst * P.nscalars + P.sumsq_slot, ss);
+    }
+}
+
 template <int M, int MODE>
 __global__ void __launch_bounds__(kIirThreads)
 k_iir(const __grid_constant__ IirParams P) {
@@ -127,11 +317,13 @@ k_iir(const __grid_constant__ IirParams P) {
 
     Cascade<M> f;
     f.init(P);
-    if (MODE == IIR_FIX) {
+    if (MODE == IIR_FIX && mychunk >= 1) {
+        const double* sin_ = P.carry_is_shift ? P.state_zs : P.state_in;
+        const int64_t src = P.carry_is_shift ? slot - 1 : slot;
 #pragma unroll
         for (int j = 0; j < M; ++j) {
-            f.s1[j] = P.state_in[(2 * j) * nslots + slot];
-            f.s2[j] = P.state_in[(2 * j + 1) * nslots + slot];
+            f.s1[j] = sin_[(2 * j) * nslots + src];
+            f.s2[j] = sin_[(2 * j + 1) * nslots + src];
         }
     }
 

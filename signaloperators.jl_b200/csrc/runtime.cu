@@ -141,6 +141,10 @@ struct IirDerived {
     bool plain_in = false;
     int plain_buf = -1;
     int64_t plain_len = 0;
+    bool fast = false;             // k_iir_fast applies (f64 in/out, constant-gain epilogue)
+    bool unitb = false;            // every section has b0 == 1 and b2 == 1 exactly
+    int n_scale = 0;
+    double scale[2] = {1.0, 1.0};
 };
 
 struct FirDerived {
@@ -309,6 +313,8 @@ void derive_iir(sigops_plan& p, StageRT& s, int idx) {
     double c[kIirMaxSections][5];
     for (int j = 0; j < st.n_sections; ++j)
         for (int k = 0; k < 5; ++k) c[j][k] = t[j * 5 + k];
+    s.iir.unitb = true;
+    for (int j = 0; j < st.n_sections; ++j) s.iir.unitb = s.iir.unitb && c[j][0] == 1.0 && c[j][2] == 1.0;
     s.iir.W = decay_length(c, st.n_sections, st.gain, std::max<int64_t>(32, std::min<int64_t>(st.n_out, 1 << 18)));
     if (st.in_prog_len == 1) {
         const sigops_instr& I = p.instrs[st.in_prog_start];
@@ -319,6 +325,19 @@ void derive_iir(sigops_plan& p, StageRT& s, int idx) {
             s.iir.plain_len = I.i1;
         }
     }
+    // FAST path: Float64 buffer in, Float64 out, epilogue = LOAD STAGE (MUL CONST){0,2}
+    bool epi_ok = st.epi_prog_len == 0;
+    if (st.epi_prog_len >= 1 && st.epi_prog_len <= 3) {
+        const sigops_instr* E = &p.instrs[st.epi_prog_start];
+        epi_ok = E[0].op == SIGOPS_OP_LOAD && E[0].leaf == SIGOPS_LEAF_STAGE;
+        for (int i = 1; i < st.epi_prog_len && epi_ok; ++i) {
+            epi_ok = E[i].op == SIGOPS_OP_MUL && E[i].leaf == SIGOPS_LEAF_CONST;
+            if (epi_ok) s.iir.scale[s.iir.n_scale++] = E[i].d0;
+        }
+        if (!epi_ok) s.iir.n_scale = 0;
+    }
+    s.iir.fast = epi_ok && s.iir.plain_in && p.bufs[s.iir.plain_buf].dtype == SIGOPS_F64 &&
+                 p.bufs[st.out_buf].dtype == SIGOPS_F64;
 }
 
 constexpr size_t kFirSmemLimit = 200 * 1024;
@@ -537,6 +556,7 @@ IirLaunch choose_iir_chunking(const StageRT& s, int64_t rows, int sm_count) {
     auto Lof = [&](int b) { return std::max<int64_t>(32, round_up((N + (int64_t)b * kIirThreads - 1) / ((int64_t)b * kIirThreads), 32)); };
     const int64_t Lmin = std::max<int64_t>(256, std::min<int64_t>(4 * W32, 8192));
     while (rows * bpr < target_blocks && Lof(bpr * 2) >= Lmin && bpr < 4096) bpr *= 2;
+    if (const char* e = getenv("SIGOPS_IIR_BPR")) bpr = std::max(1, atoi(e));   // tuning knob
     IirLaunch r;
     r.blocks_per_row = bpr;
     r.L = Lof(bpr);
@@ -578,6 +598,22 @@ size_t wave_workspace_bytes(const sigops_plan& p, int64_t ninst, int sm_count) {
     return temp_bytes_per_instance(p) * ninst + iir_state_bytes(p, ninst, sm_count) +
            (size_t)ninst * p.nbuf() * sizeof(BufRef) + (size_t)ninst * std::max<uint32_t>(p.h.n_scalars, 1) * sizeof(double) +
            (1 << 16);
+}
+
+template <int MODE>
+void launch_iir_fast(int M, bool unitb, dim3 grid, cudaStream_t st, const IirParams& P) {
+#define SIGOPS_IIR_CASE(m)                                                  \
+    case m:                                                                 \
+        if (unitb) k_iir_fast<m, MODE, true><<<grid, kIirThreads, 0, st>>>(P);  \
+        else k_iir_fast<m, MODE, false><<<grid, kIirThreads, 0, st>>>(P);       \
+        break;
+    switch (M) {
+        SIGOPS_IIR_CASE(1) SIGOPS_IIR_CASE(2) SIGOPS_IIR_CASE(3) SIGOPS_IIR_CASE(4)
+        SIGOPS_IIR_CASE(5) SIGOPS_IIR_CASE(6) SIGOPS_IIR_CASE(7) SIGOPS_IIR_CASE(8)
+        default: fail(SIGOPS_ERR_UNSUPPORTED, "IIR cascade of %d sections", M);
+    }
+#undef SIGOPS_IIR_CASE
+    CUDA_OK(cudaGetLastError());
 }
 
 template <int MODE>
@@ -706,18 +742,21 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
             const int S = 2 * s.iir.M;
             P.state_zs = (double*)slot.arena.take(nslots * S * sizeof(double));
             P.state_in = (double*)slot.arena.take(nslots * S * sizeof(double));
+            P.n_epi_scale = s.iir.n_scale;
+            P.epi_scale[0] = s.iir.scale[0]; P.epi_scale[1] = s.iir.scale[1];
+            P.carry_is_shift = c.need_matrix ? 0 : 1;
             dim3 grid((unsigned)(rows * c.blocks_per_row));
             {
                 ProfScope ps(slot, p.ctx->profiling, stream, KIND_IIR_MAIN);
-                launch_iir<IIR_MAIN>(s.iir.M, grid, stack_iir, stream, P);
+                if (s.iir.fast) launch_iir_fast<IIR_MAIN>(s.iir.M, s.iir.unitb, grid, stream, P);
+                else launch_iir<IIR_MAIN>(s.iir.M, grid, stack_iir, stream, P);
             }
             ++launches;
             if (c.nchunks > 1) {
-                CarryParams C{};
-                C.state_zs = P.state_zs; C.state_in = P.state_in;
-                C.nrows = rows; C.slots_per_row = P.slots_per_row; C.nchunks = c.nchunks; C.M2 = S;
-                C.AL = nullptr;
                 if (c.need_matrix) {
+                    CarryParams C{};
+                    C.state_zs = P.state_zs; C.state_in = P.state_in;
+                    C.nrows = rows; C.slots_per_row = P.slots_per_row; C.nchunks = c.nchunks; C.M2 = S;
                     double cc[kIirMaxSections][5];
                     for (int j = 0; j < s.iir.M; ++j)
                         for (int k = 0; k < 5; ++k) cc[j][k] = P.coef[j][k];
@@ -726,17 +765,17 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                     CUDA_OK(cudaMemcpyAsync(dAL, AL.data(), AL.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
                     CUDA_OK(cudaStreamSynchronize(stream));   // AL is a host temporary
                     C.AL = dAL;
-                }
-                {
                     ProfScope ps(slot, p.ctx->profiling, stream, KIND_IIR_CARRY);
                     k_iir_carry<<<(unsigned)((rows + 127) / 128), 128, 0, stream>>>(C);
+                    CUDA_OK(cudaGetLastError());
+                    ++launches;
                 }
-                CUDA_OK(cudaGetLastError());
                 {
                     ProfScope ps(slot, p.ctx->profiling, stream, KIND_IIR_FIX);
-                    launch_iir<IIR_FIX>(s.iir.M, grid, stack_iir, stream, P);
+                    if (s.iir.fast) launch_iir_fast<IIR_FIX>(s.iir.M, s.iir.unitb, grid, stream, P);
+                    else launch_iir<IIR_FIX>(s.iir.M, grid, stack_iir, stream, P);
                 }
-                launches += 2;
+                ++launches;
             }
         } else {
             if (g.n_out == 0) continue;
