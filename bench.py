@@ -192,7 +192,10 @@ def run_gpu(args, rank, world, local_rank):
             arr[i] = cabi.Buffer(t[i].data_ptr(), NFRAMES, NCH, cabi.F64, NFRAMES)
         return arr
     ins, outs = bufs(x), bufs(y)
-    stream = torch.cuda.current_stream()
+    # a real (non-legacy) stream: handle 0 would mean "library stream + synchronise" to the C ABI
+    torch.cuda.synchronize()
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
 
     def step():
         cp.run_device(NINST, ins, outs, stream=stream.cuda_stream)

@@ -60,7 +60,7 @@ struct IirParams {
     int carry_is_shift;        // FIX reads s_in[k] = state_zs[k-1] directly (no CARRY launch)
 };
 
-enum { IIR_MAIN = 0, IIR_FIX = 1 };
+enum { IIR_MAIN = 0, IIR_FIX = 1, IIR_WARM = 2 };
 
 template <int M>
 struct Cascade {

@@ -4,12 +4,15 @@
 // sharding over devices (no collectives: instances are independent, SURVEY.md
 // §8e) and the host<->device pipeline of `sigops_plan_run`.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <unordered_map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -21,6 +24,7 @@
 #include "../../include/signalops.h"
 #include "k_fir.cuh"
 #include "k_iir.cuh"
+#include "k_iir_tma.cuh"
 #include "k_map.cuh"
 
 static_assert(sizeof(sigops_instr) == 80, "ABI: sigops_instr");
@@ -57,6 +61,21 @@ struct Failure {
                  "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__,   \
                  cudaGetErrorString(e__));                                                  \
     } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device, size)
+std::mutex g_attr_mu;
+std::unordered_map<const void*, std::pair<uint64_t, size_t>> g_attr_done;
+template <class K>
+void ensure_dyn_smem(K kernel, size_t bytes) {
+    int devno = 0;
+    cudaGetDevice(&devno);
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    auto& e = g_attr_done[(const void*)kernel];
+    if ((e.first >> (devno & 63) & 1) && e.second >= bytes) return;
+    CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    e.first |= uint64_t(1) << (devno & 63);
+    e.second = std::max(e.second, bytes);
+}
 
 size_t elem_size(int dtype) { return dtype == SIGOPS_F32 ? 4 : 8; }
 int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
@@ -96,6 +115,14 @@ struct Slot {
     void* last_table_dev = nullptr;
     cudaEvent_t ev[6] = {};
     // per-launch timing (sigops_ctx_set_profiling): (start, stop, kernel kind)
+    // prepared launches of the last wave (replayed when the same plan runs on the same buffers)
+    struct Prepared {
+        int kind;
+        std::function<void(cudaStream_t)> fn;
+    };
+    std::vector<Prepared> cache_launches;
+    uint64_t cache_plan = 0;      // plan uid
+    int64_t cache_ninst = -1;
     std::vector<cudaEvent_t> prof_pool;
     std::vector<int> prof_kind;
     size_t prof_used = 0;
@@ -191,6 +218,7 @@ struct sigops_plan {
     std::vector<PlanDev> dev;
     int nbuf() const { return (int)bufs.size(); }
     int max_stack = 0;
+    uint64_t uid = 0;
 };
 
 namespace {
@@ -548,6 +576,37 @@ struct IirLaunch {
     bool need_matrix;
 };
 
+// Chunking for k_iir_tma: chunks are numbered over all rows jointly, so L can be chosen
+// freely (multiple of the 64-frame stage).  Cost model: a block's time is proportional to
+// the frames one lane walks (L in MAIN, min(W,L) in FIX) and blocks run in whole waves
+// of one block per SM.
+IirLaunch choose_iir_chunking_flat(const StageRT& s, int64_t rows, int sm_count) {
+    const int64_t N = s.st.n_out;
+    const int64_t W64 = round_up(std::max<int64_t>(s.iir.W, 1), kStageCols);
+    const int64_t jmax = std::max<int64_t>(1, (N + kStageCols - 1) / kStageCols);
+    double best = 1e300;
+    int64_t bestL = kStageCols * jmax;
+    const int64_t step = std::max<int64_t>(1, jmax / 4096);
+    for (int64_t j = 1; j <= jmax; j += step) {
+        const int64_t L = j * kStageCols;
+        const int64_t cpr = (N + L - 1) / L;
+        const int64_t blocks = (((rows * cpr) + 31) / 32 + kTmaWarps - 1) / kTmaWarps;
+        const int64_t waves = (blocks + sm_count - 1) / sm_count;
+        const double fix = cpr > 1 ? (double)std::min(W64, L) * (W64 >= L ? 1.0 : 1.2) : 0.0;
+        double cost = (double)waves * ((double)L + fix + 600.0);      // + fixed per-wave cost (launch, pipeline fill)
+        if (N % L) cost *= 1.02;                                     // ragged last chunk takes the scalar path
+        if (cost < best) { best = cost; bestL = L; }
+    }
+    if (const char* e = getenv("SIGOPS_IIR_L")) bestL = std::max<int64_t>(kStageCols, round_up(atoll(e), kStageCols));
+    IirLaunch r;
+    r.blocks_per_row = 0;
+    r.L = bestL;
+    r.nchunks = (N + bestL - 1) / bestL;
+    r.Wc = std::min(W64, r.L);
+    r.need_matrix = s.iir.W >= r.L;
+    return r;
+}
+
 IirLaunch choose_iir_chunking(const StageRT& s, int64_t rows, int sm_count) {
     const int64_t N = s.st.n_out;
     const int64_t W32 = round_up(std::max<int64_t>(s.iir.W, 1), 32);
@@ -588,8 +647,10 @@ size_t iir_state_bytes(const sigops_plan& p, int64_t ninst, int sm_count) {
     for (auto& s : p.stages) {
         if (s.st.kind != SIGOPS_STAGE_IIR) continue;
         const int64_t rows = ninst * s.st.nchannels;
-        IirLaunch c = choose_iir_chunking(s, rows, sm_count);
-        total += (size_t)2 * (2 * s.iir.M) * rows * c.blocks_per_row * kIirThreads * sizeof(double) + 4096 + 1024;
+        const IirLaunch a = choose_iir_chunking(s, rows, sm_count);
+        size_t slots = (size_t)rows * a.blocks_per_row * kIirThreads;
+        if (s.iir.fast) slots = std::max(slots, (size_t)rows * choose_iir_chunking_flat(s, rows, sm_count).nchunks);
+        total += (size_t)2 * (2 * s.iir.M) * slots * sizeof(double) + 4096 + 1024;
     }
     return total;
 }
@@ -616,11 +677,34 @@ void launch_iir_fast(int M, bool unitb, dim3 grid, cudaStream_t st, const IirPar
     CUDA_OK(cudaGetLastError());
 }
 
+constexpr size_t kTmaSmemBytes = (size_t)kTmaThreads * 2 * kStagePitch * sizeof(double) + (size_t)kTmaThreads * 2 * sizeof(uint64_t);
+
+template <int MODE>
+void launch_iir_tma(int M, bool unitb, dim3 grid, cudaStream_t st, const IirTmaParams& Q) {
+#define SIGOPS_IIR_CASE(m)                                                                                          \
+    case m:                                                                                                         \
+        if (unitb) {                                                                                                \
+            ensure_dyn_smem(k_iir_tma<m, MODE, true>, kTmaSmemBytes); \
+            k_iir_tma<m, MODE, true><<<grid, kTmaThreads, kTmaSmemBytes, st>>>(Q);                                   \
+        } else {                                                                                                    \
+            ensure_dyn_smem(k_iir_tma<m, MODE, false>, kTmaSmemBytes); \
+            k_iir_tma<m, MODE, false><<<grid, kTmaThreads, kTmaSmemBytes, st>>>(Q);                                  \
+        }                                                                                                           \
+        break;
+    switch (M) {
+        SIGOPS_IIR_CASE(1) SIGOPS_IIR_CASE(2) SIGOPS_IIR_CASE(3) SIGOPS_IIR_CASE(4)
+        SIGOPS_IIR_CASE(5) SIGOPS_IIR_CASE(6) SIGOPS_IIR_CASE(7) SIGOPS_IIR_CASE(8)
+        default: fail(SIGOPS_ERR_UNSUPPORTED, "IIR cascade of %d sections", M);
+    }
+#undef SIGOPS_IIR_CASE
+    CUDA_OK(cudaGetLastError());
+}
+
 template <int MODE>
 void launch_iir(int M, dim3 grid, size_t smem, cudaStream_t st, const IirParams& P) {
 #define SIGOPS_IIR_CASE(m)                                                                                 \
     case m:                                                                                                \
-        if (smem > 0) CUDA_OK(cudaFuncSetAttribute(k_iir<m, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        if (smem > 0) ensure_dyn_smem(k_iir<m, MODE>, smem); \
         k_iir<m, MODE><<<grid, kIirThreads, smem, st>>>(P);                                                \
         break;
     switch (M) {
@@ -639,8 +723,6 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
     const int nbuf = p.nbuf();
     const int64_t ninst = io.ninst;
     const int nscal = std::max<uint32_t>(p.h.n_scalars, 1);
-    int64_t launches = 0;
-
     // -- workspace carve-up
     const size_t temp_stride = temp_bytes_per_instance(p);
     char* temps = temp_stride ? (char*)slot.arena.take(temp_stride * ninst) : nullptr;
@@ -678,6 +760,7 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
             }
         }
     }
+    bool table_changed = false;
     if (slot.last_table_dev != (void*)d_refs || slot.last_table != table) {
         // the pinned staging buffer may still be in flight from the previous wave of this slot
         CUDA_OK(cudaStreamSynchronize(stream));
@@ -685,7 +768,22 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
         CUDA_OK(cudaMemcpyAsync(d_refs, slot.pinned, table_bytes, cudaMemcpyHostToDevice, stream));
         slot.last_table.swap(table);
         slot.last_table_dev = d_refs;
+        table_changed = true;
     }
+    // Same plan on the same buffers as last time: replay the prepared launches (all the
+    // chunking / alignment / table decisions below are pure functions of those).
+    auto replay = [&]() -> int64_t {
+        for (auto& L : slot.cache_launches) {
+            ProfScope ps(slot, p.ctx->profiling, stream, L.kind);
+            L.fn(stream);
+            CUDA_OK(cudaGetLastError());
+        }
+        return (int64_t)slot.cache_launches.size();
+    };
+    if (!table_changed && slot.cache_plan == p.uid && slot.cache_ninst == ninst) return replay();
+    slot.cache_launches.clear();
+    slot.cache_plan = 0;
+    auto add = [&](int kind, std::function<void(cudaStream_t)> fn) { slot.cache_launches.push_back({kind, std::move(fn)}); };
 
     const size_t stack_map = p.max_stack ? (size_t)p.max_stack * kMapV * kMapThreads * sizeof(double) : 0;
     const size_t stack_iir = p.max_stack ? (size_t)p.max_stack * kIirV * kIirThreads * sizeof(double) : 0;
@@ -707,22 +805,28 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
             }
             P.tile_prefix[g.n_pieces] = tiles;
             if (tiles == 0) continue;
-            if (stack_map > 16 * 1024) CUDA_OK(cudaFuncSetAttribute(k_map, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stack_map));
+            if (stack_map > 16 * 1024) ensure_dyn_smem(k_map, stack_map);
             for (int64_t i0 = 0; i0 < ninst; i0 += 65535) {
                 const int64_t ni = std::min<int64_t>(65535, ninst - i0);
                 MapParams Q = P;
                 Q.bufrefs = d_refs + i0 * nbuf;
                 Q.scalars = scalars + i0 * nscal;
                 dim3 grid(tiles, P.out_nch, (unsigned)ni);
-                ProfScope ps(slot, p.ctx->profiling, stream, KIND_MAP);
-                k_map<<<grid, kMapThreads, stack_map, stream>>>(Q);
-                CUDA_OK(cudaGetLastError());
-                ++launches;
+                add(KIND_MAP, [=](cudaStream_t st) { k_map<<<grid, kMapThreads, stack_map, st>>>(Q); });
             }
         } else if (g.kind == SIGOPS_STAGE_IIR) {
             if (g.n_out == 0) continue;
             const int64_t rows = ninst * g.nchannels;
-            const IirLaunch c = choose_iir_chunking(s, rows, dev.sm_count);
+            // TMA path: fast-path stage whose every channel starts on a 16-byte boundary
+            bool tma = s.iir.fast && !getenv("SIGOPS_NO_TMA");
+            if (tma) {
+                for (int64_t i = 0; i < ninst && tma; ++i)
+                    for (int b : {s.iir.plain_buf, g.out_buf}) {
+                        const BufRef& rb = ((const BufRef*)slot.last_table.data())[i * nbuf + b];
+                        if (((uintptr_t)rb.ptr & 15) || (rb.nch > 1 && (rb.ld & 1))) tma = false;
+                    }
+            }
+            const IirLaunch c = tma ? choose_iir_chunking_flat(s, rows, dev.sm_count) : choose_iir_chunking(s, rows, dev.sm_count);
             IirParams P{};
             P.instrs = pd.instrs; P.bufrefs = d_refs; P.scalars = scalars;
             P.nbuf = nbuf; P.nscalars = nscal;
@@ -733,7 +837,7 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
             P.plain_in_len = s.iir.plain_len;
             P.nch = g.nchannels; P.blocks_per_row = c.blocks_per_row;
             P.N = g.n_out; P.L = c.L; P.Wc = c.Wc;
-            P.slots_per_row = (int64_t)c.blocks_per_row * kIirThreads;
+            P.slots_per_row = tma ? c.nchunks : (int64_t)c.blocks_per_row * kIirThreads;
             P.M = s.iir.M; P.gain = g.gain;
             const double* t = p.blob.data() + p.tables[g.coef_table].offset;
             for (int j = 0; j < s.iir.M; ++j)
@@ -745,14 +849,26 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
             P.n_epi_scale = s.iir.n_scale;
             P.epi_scale[0] = s.iir.scale[0]; P.epi_scale[1] = s.iir.scale[1];
             P.carry_is_shift = c.need_matrix ? 0 : 1;
-            dim3 grid((unsigned)(rows * c.blocks_per_row));
+            IirTmaParams Q{};
+            Q.base = P; Q.cpr = c.nchunks; Q.total_chunks = rows * c.nchunks;
+            if (getenv("SIGOPS_DEBUG"))
+                fprintf(stderr, "[sigops] IIR stage %zu: %s rows=%lld N=%lld M=%d W=%lld L=%lld chunks/row=%lld Wc=%lld matrix=%d\n", si,
+                        tma ? "tma" : (s.iir.fast ? "cp.async" : "generic"), (long long)rows, (long long)g.n_out, s.iir.M,
+                        (long long)s.iir.W, (long long)c.L, (long long)c.nchunks, (long long)c.Wc, (int)c.need_matrix);
+            const int64_t tma_blocks = ((Q.total_chunks + 31) / 32 + kTmaWarps - 1) / kTmaWarps;
+            dim3 grid((unsigned)(tma ? tma_blocks : rows * c.blocks_per_row));
+            const bool warm = tma && !c.need_matrix;     // single self-contained launch
             {
-                ProfScope ps(slot, p.ctx->profiling, stream, KIND_IIR_MAIN);
-                if (s.iir.fast) launch_iir_fast<IIR_MAIN>(s.iir.M, s.iir.unitb, grid, stream, P);
-                else launch_iir<IIR_MAIN>(s.iir.M, grid, stack_iir, stream, P);
+                const int M_ = s.iir.M;
+                const bool unitb = s.iir.unitb, fast = s.iir.fast;
+                add(KIND_IIR_MAIN, [=](cudaStream_t st) {
+                    if (warm) launch_iir_tma<IIR_WARM>(M_, unitb, grid, st, Q);
+                    else if (tma) launch_iir_tma<IIR_MAIN>(M_, unitb, grid, st, Q);
+                    else if (fast) launch_iir_fast<IIR_MAIN>(M_, unitb, grid, st, P);
+                    else launch_iir<IIR_MAIN>(M_, grid, stack_iir, st, P);
+                });
             }
-            ++launches;
-            if (c.nchunks > 1) {
+            if (c.nchunks > 1 && !warm) {
                 if (c.need_matrix) {
                     CarryParams C{};
                     C.state_zs = P.state_zs; C.state_in = P.state_in;
@@ -765,17 +881,18 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                     CUDA_OK(cudaMemcpyAsync(dAL, AL.data(), AL.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
                     CUDA_OK(cudaStreamSynchronize(stream));   // AL is a host temporary
                     C.AL = dAL;
-                    ProfScope ps(slot, p.ctx->profiling, stream, KIND_IIR_CARRY);
-                    k_iir_carry<<<(unsigned)((rows + 127) / 128), 128, 0, stream>>>(C);
-                    CUDA_OK(cudaGetLastError());
-                    ++launches;
+                    const unsigned cblocks = (unsigned)((rows + 127) / 128);
+                    add(KIND_IIR_CARRY, [=](cudaStream_t st) { k_iir_carry<<<cblocks, 128, 0, st>>>(C); });
                 }
                 {
-                    ProfScope ps(slot, p.ctx->profiling, stream, KIND_IIR_FIX);
-                    if (s.iir.fast) launch_iir_fast<IIR_FIX>(s.iir.M, s.iir.unitb, grid, stream, P);
-                    else launch_iir<IIR_FIX>(s.iir.M, grid, stack_iir, stream, P);
+                    const int M_ = s.iir.M;
+                    const bool unitb = s.iir.unitb, fast = s.iir.fast;
+                    add(KIND_IIR_FIX, [=](cudaStream_t st) {
+                        if (tma) launch_iir_tma<IIR_FIX>(M_, unitb, grid, st, Q);
+                        else if (fast) launch_iir_fast<IIR_FIX>(M_, unitb, grid, st, P);
+                        else launch_iir<IIR_FIX>(M_, grid, stack_iir, st, P);
+                    });
                 }
-                ++launches;
             }
         } else {
             if (g.n_out == 0) continue;
@@ -800,22 +917,23 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
             const int64_t groups = (rows + 32 * G - 1) / (32 * G);
             if (groups > 65535) fail(SIGOPS_ERR_UNSUPPORTED, "FIR stage over more than %d rows per wave", 65535 * 32 * G);
             dim3 grid((unsigned)tiles, (unsigned)groups);
-            ProfScope ps(slot, p.ctx->profiling, stream, KIND_FIR);
-            if (G == 4) {
-                CUDA_OK(cudaFuncSetAttribute(k_fir<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_fir<4><<<grid, kFirThreads, smem, stream>>>(P);
-            } else if (G == 2) {
-                CUDA_OK(cudaFuncSetAttribute(k_fir<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_fir<2><<<grid, kFirThreads, smem, stream>>>(P);
-            } else {
-                CUDA_OK(cudaFuncSetAttribute(k_fir<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_fir<1><<<grid, kFirThreads, smem, stream>>>(P);
-            }
-            CUDA_OK(cudaGetLastError());
-            ++launches;
+            add(KIND_FIR, [=](cudaStream_t st) {
+                if (G == 4) {
+                    ensure_dyn_smem(k_fir<4>, smem);
+                    k_fir<4><<<grid, kFirThreads, smem, st>>>(P);
+                } else if (G == 2) {
+                    ensure_dyn_smem(k_fir<2>, smem);
+                    k_fir<2><<<grid, kFirThreads, smem, st>>>(P);
+                } else {
+                    ensure_dyn_smem(k_fir<1>, smem);
+                    k_fir<1><<<grid, kFirThreads, smem, st>>>(P);
+                }
+            });
         }
     }
-    return launches;
+    slot.cache_plan = p.uid;
+    slot.cache_ninst = ninst;
+    return replay();
 }
 
 void validate_io(const sigops_plan& p, int64_t ninst, const sigops_buffer* in, const sigops_buffer* out) {
@@ -1101,6 +1219,8 @@ int sigops_plan_create(sigops_ctx* ctx, const void* plan, size_t nbytes, sigops_
         if (!ctx || !plan || !out) fail(SIGOPS_ERR_INVALID, "null argument");
         *out = nullptr;
         auto p = std::make_unique<sigops_plan>();
+        static std::atomic<uint64_t> next_uid{1};
+        p->uid = next_uid++;
         p->ctx = ctx;
         parse_plan(*p, plan, nbytes);
         p->dev.resize(ctx->devs.size());

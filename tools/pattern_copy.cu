@@ -50,6 +50,76 @@ __global__ void __launch_bounds__(128) k_pattern(const double* __restrict__ x, d
     }
 }
 
+// per-lane streams moved by TMA bulk copies (the k_iir_tma data path, no compute)
+__device__ __forceinline__ unsigned su32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int COLS>
+__global__ void __launch_bounds__(192, 1) k_bulk(const double* __restrict__ x, double* __restrict__ y, int64_t L, int64_t nchunks) {
+    extern __shared__ __align__(128) unsigned char raw[];
+    constexpr int PITCH = COLS + 2;
+    const int tid = threadIdx.x;
+    double* st0 = reinterpret_cast<double*>(raw) + (size_t)tid * PITCH;
+    double* st1 = st0 + (size_t)192 * PITCH;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(raw) + (size_t)192 * 2 * PITCH) + tid * 2;
+    const int64_t g = (int64_t)blockIdx.x * 192 + tid;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(su32(&bars[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(su32(&bars[1])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (g >= nchunks) return;
+    const double* src = x + g * L;
+    double* dst = y + g * L;
+    const int64_t nst = L / COLS;
+    unsigned par = 0;
+    auto load = [&](int64_t h) {
+        const unsigned b = h & 1;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(su32(&bars[b])), "r"(COLS * 8) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(su32(b ? st1 : st0)),
+                     "l"(src + h * COLS), "r"(COLS * 8), "r"(su32(&bars[b])) : "memory");
+    };
+    load(0);
+    for (int64_t h = 0; h < nst; ++h) {
+        const unsigned b = h & 1;
+        double* buf = b ? st1 : st0;
+        asm volatile("{\n.reg .pred p;\nLW:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra LD;\nbra LW;\nLD:\n}\n" ::"r"(su32(&bars[b])), "r"((par >> b) & 1u) : "memory");
+        par ^= 1u << b;
+        if (h + 1 < nst) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            load(h + 1);
+        }
+        for (int i = 0; i < COLS; i += 2) {
+            double2 v = *reinterpret_cast<double2*>(buf + i);
+            v.x *= 1.5; v.y *= 1.5;
+            *reinterpret_cast<double2*>(buf + i) = v;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + h * COLS), "r"(su32(buf)), "r"(COLS * 8) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <int COLS>
+void run_bulk(const double* x, double* y, int64_t n, int64_t L) {
+    const int64_t chunks = n / L;
+    const int blocks = (int)((chunks + 191) / 192);
+    const size_t smem = (size_t)192 * 2 * (COLS + 2) * 8 + 192 * 16;
+    cudaFuncSetAttribute(k_bulk<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e9;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        k_bulk<COLS><<<blocks, 192, smem>>>(x, y, L, chunks);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep && ms < best) best = ms;
+    }
+    printf("per-lane TMA bulk %4d B stages   L=%6lld blocks=%5d smem/blk=%6zu : %.3f ms  %.0f GB/s  (%s)\n", COLS * 8, (long long)L, blocks, smem, best,
+           2.0 * n * 8 / best / 1e6, cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int COLS, int NBUF>
 void run(const double* x, double* y, int64_t n, int64_t L, const char* name) {
     const int64_t chunks = n / L;
@@ -86,7 +156,12 @@ int main() {
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (rep == 2) printf("plain grid-stride copy: %.3f ms %.0f GB/s\n", ms, 2.0 * n * 8 / ms / 1e6);
     }
-    for (int64_t L : {3776LL, 1888LL, 960LL}) {
+    for (int64_t L : {8704LL, 4352LL, 2176LL}) {
+        run_bulk<32>(x, y, n, L);
+        run_bulk<64>(x, y, n, L);
+        run_bulk<128>(x, y, n, L);
+    }
+    for (int64_t L : {3776LL}) {
         run<16, 2>(x, y, n, L, "16 cols (128B), 2 buffers");
         run<32, 1>(x, y, n, L, "32 cols (256B), 1 buffer");
         run<32, 2>(x, y, n, L, "32 cols (256B), 2 buffers");

@@ -36,7 +36,9 @@ x = torch.randn((ninst, nch, nin), dtype=torch.float64, device="cuda")
 y = torch.empty((ninst, nch, nout), dtype=torch.float64, device="cuda")
 ins = (cabi.Buffer * ninst)(*[cabi.Buffer(x[i].data_ptr(), nin, nch, cabi.F64, nin) for i in range(ninst)])
 outs = (cabi.Buffer * ninst)(*[cabi.Buffer(y[i].data_ptr(), nout, nch, cabi.F64, nout) for i in range(ninst)])
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream()
+torch.cuda.synchronize()
+torch.cuda.set_stream(stream)
 ctx.set_profiling(True)
 for _ in range(2):
     cp.run_device(ninst, ins, outs, stream=stream.cuda_stream)
@@ -44,13 +46,15 @@ torch.cuda.synchronize()
 ctx.profile_collect(0)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
+h0 = time.perf_counter()
 for _ in range(steps):
     cp.run_device(ninst, ins, outs, stream=stream.cuda_stream)
+host_ms = (time.perf_counter() - h0) * 1e3 / steps
 e1.record()
 torch.cuda.synchronize()
 t = e0.elapsed_time(e1) / steps
 prof = ctx.profile_collect(0)
 samples = ninst * nch * nout
-print(f"{cfg}: {t:.3f} ms/step, {samples / t / 1e3:.0f} Msamples/s, alg bytes {cp.algorithmic_bytes() * ninst / 1e9:.3f} GB "
+print(f"{cfg}: host enqueue {host_ms:.3f} ms/step; {t:.3f} ms/step, {samples / t / 1e3:.0f} Msamples/s, alg bytes {cp.algorithmic_bytes() * ninst / 1e9:.3f} GB "
       f"-> {cp.algorithmic_bytes() * ninst / t / 1e6:.0f} GB/s; kernels/step "
       + ", ".join(f"{k}={v[0] / steps:.3f}ms" for k, v in prof.items()))
