@@ -67,43 +67,52 @@ def ncu_traffic():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons polled through NVML in a background thread DURING the
+    timed region (the same counters `nvidia-smi --query-gpu=clocks.sm,...` prints)."""
 
     def __init__(self, gpu_index):
-        self.p = None
+        import threading
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._ok = False
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE,
-                                      stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._ok = True
+        except Exception as e:                                   # pragma: no cover
+            self.err = repr(e)
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        if not self._ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.05)
-        self.p.terminate()
-        try:
-            out, _ = self.p.communicate(timeout=5)
-        except Exception:
-            self.p.kill()
-            out = ""
-        sm, mx, reasons = [], [], set()
-        for line in out.splitlines():
-            f = [t.strip() for t in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self._stop.set()
+        self.t.join(timeout=2)
+        if not self._ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.samples), "reasons": sorted(self.reasons)}
 
 
 def cpu_baseline(seconds_target=12.0, threads=None):
@@ -268,7 +277,11 @@ def run_gpu(args, rank, world, local_rank):
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_ok = bool(torch.equal(yh[0], y[0].cpu()))
+    # waves of the host path are chunked differently from the 256-instance device run, so the two
+    # results agree to rounding, not bit for bit
+    ref0 = y[0].cpu()
+    e2e_err = float((yh[0] - ref0).abs().max() / ref0.pow(2).mean().sqrt())
+    e2e_ok = bool(e2e_err < 1e-9)
     e2e_value = world * samples_step * e2e_steps / e2e_s / 1e6
 
     if rank == 0:
@@ -289,10 +302,10 @@ def run_gpu(args, rank, world, local_rank):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(st.h2d_bytes),
                     "d2h_bytes_per_step": int(st.d2h_bytes), "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
-                    "matches_device_run": e2e_ok,
+                    "matches_device_run": e2e_ok, "max_err_over_rms_vs_device_run": e2e_err,
                     "h2d_ms": st.h2d_ms, "kernels_ms": st.gpu_ms, "d2h_ms": st.d2h_ms},
             "gpu_launches": int(sum(n for _, n in prof.values())),
-            "roofline": {"bound": "hbm", "kernel": "k_iir<4,MAIN>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_iir_tma<4,WARM,unitb>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "launch_ms": main_ms / max(main_n, 1),
