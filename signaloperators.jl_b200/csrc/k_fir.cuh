@@ -14,17 +14,22 @@
 //             the integer phase of the rational kernels
 // so  y[m] = sum_t (pfb[phiIdx][t] + alpha*dpfb[phiIdx][t]) * x[xi0 - tapsPerPhi + 1 + t].
 //
-// Block = tile of T outputs x RB rows (a row = one channel of one instance).
-// The taps of the tile's outputs are merged once into shared memory and reused
-// by all RB rows; the input window of the tile is staged transposed
-// ([position][row]) so lanes = rows read it conflict-free; each thread keeps an
-// 8-output x 4-row accumulator tile in registers, so one broadcast tap load
-// feeds 4 FMAs and one sample load feeds 8.
+// Block = tile of 64 outputs x RB = 32*G rows (a row = one channel of one instance).
+//   * merged taps of the tile's outputs: built once in shared memory, shared by all rows,
+//     each row of the table placed so that tap pairs are 16-byte aligned with the
+//     (even) window position they multiply
+//   * input window: cp.async global -> shared, layout [row][position] (coalesced 256-byte
+//     reads, conflict-free 128-bit reads with lanes = rows)
+//   * thread = 8 outputs x G rows register tile; per pair of window positions it issues
+//     G 128-bit sample loads + 8 128-bit broadcast tap loads for 16*G FMAs
+//   * results staged [row][output] and written back as coalesced 512-byte rows, through
+//     the fused epilogue program when there is one.
 //
 // Roofline (44.1k -> 48k): 15.35 B per output sample of HBM traffic, 38 FP64
 // FMAs per sample after merging.
 #pragma once
 #include "interp.cuh"
+#include "k_iir.cuh"   // cp_async8 / cp_async_wait_all
 
 namespace sigops {
 
@@ -32,7 +37,7 @@ constexpr int kFirWarps = 8;
 constexpr int kFirThreads = kFirWarps * 32;
 constexpr int kFirR = 8;                    // outputs per thread
 constexpr int kFirT = kFirWarps * kFirR;    // outputs per tile (64)
-// rows per thread G in {1,2,4}: rows per block RB = 32*G, smem row pitch RB+1
+constexpr int kFirYPitch = kFirT + 2;       // doubles; = 2 mod 16 keeps lane=row 128-bit stores conflict free
 
 struct FirParams {
     const sigops_instr* instrs;
@@ -46,120 +51,183 @@ struct FirParams {
     int nch;
     int64_t nrows;
     int64_t n_out;
-    int tapsper, dpad, tpad;   // tpad = tapsper + 2*dpad
-    int pmax;                  // max window positions of any tile
+    int tapsper;
+    int hbase;                 // even, > max window shift inside a group of 8 outputs
+    int tpad;                  // doubles per merged-tap row (even)
+    int xpitch;                // doubles per window row, = 2 mod 16, >= max positions of a tile + 2
     const double* pfb;         // [nphases][tapsper]
     const double* dpfb;        // or nullptr
     const int64_t* xi0;        // [ceil(n_out/T)*T], tail repeats the last entry
     const double* phi;
 };
 
-template <int kFirG>
+template <int G>
 __global__ void __launch_bounds__(kFirThreads)
 k_fir(const __grid_constant__ FirParams P) {
-    constexpr int kFirRB = 32 * kFirG;
-    constexpr int kFirRowPitch = kFirRB + 1;
+    constexpr int RB = 32 * G;
     __shared__ sigops_instr sprog_epi[SIGOPS_MAX_PROG];
     __shared__ double lc_epi[kFirWarps][SIGOPS_MAX_PROG];
-    __shared__ int64_t s_xi0[kFirT];
-    extern __shared__ double smem[];
-    double* hm = smem;                                   // [T][tpad]
-    double* xs = smem + (size_t)kFirT * P.tpad;          // [pmax][RB+1], later ys[T][RB+1]
-    double* stack = xs + (size_t)(P.pmax > kFirT ? P.pmax : kFirT) * kFirRowPitch;
+    __shared__ int s_ws[kFirT];                           // window start of output m relative to the tile
+    extern __shared__ __align__(16) double smem[];
+    double* hm = smem;                                    // [T][tpad]
+    double* xs = smem + (size_t)kFirT * P.tpad;           // [RB][xpitch]; reused as ys[RB][kFirYPitch]
+    const int xrows = P.xpitch > kFirYPitch ? P.xpitch : kFirYPitch;
+    double* stack = xs + (size_t)RB * xrows;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t m0 = (int64_t)blockIdx.x * kFirT;
-    const int64_t row0 = (int64_t)blockIdx.y * kFirRB;
+    const int64_t row0 = (int64_t)blockIdx.y * RB;
+    // tile window: even start so that position pairs stay 16-byte aligned
+    const int64_t p_first = P.xi0[m0] - P.tapsper + 1;
+    const int64_t p0 = p_first & ~int64_t(1);
+    const int npos = (int)(P.xi0[m0 + kFirT - 1] - p0 + 1);
 
-    for (int i = threadIdx.x; i < P.epi_prog_len; i += blockDim.x) sprog_epi[i] = P.instrs[P.epi_prog_start + i];
-    if (threadIdx.x < kFirT) s_xi0[threadIdx.x] = P.xi0[m0 + threadIdx.x];
-    // merged taps (zero outside [0,tapsper) so shifted windows need no predicate)
-    for (int i = threadIdx.x; i < kFirT * P.tpad; i += blockDim.x) {
-        const int m = i / P.tpad, t = i % P.tpad - P.dpad;
-        double h = 0.0;
-        if (t >= 0 && t < P.tapsper && m0 + m < P.n_out) {
+    // ---- 0. per-row addressing, once per block (one thread per row)
+    __shared__ const double* s_src[32 * 4];     // row base + p0 for Float64 rows, else nullptr
+    __shared__ int s_rowkind[32 * 4];           // 0 = no such row, 1 = Float64 (cp.async), 2 = other types
+    __shared__ double* s_dst[32 * 4];           // output row base when it takes aligned Float64 pair stores
+    __shared__ int s_inst[32 * 4], s_chan[32 * 4];
+    if (tid < RB) {
+        const int64_t row = row0 + tid;
+        const double* src = nullptr;
+        double* dstp = nullptr;
+        int kind = 0, inst_ = 0, c_ = 0;
+        if (row < P.nrows) {
+            const int64_t inst = row / P.nch;
+            const int c = (int)(row - inst * P.nch);
+            inst_ = (int)inst; c_ = c;
+            const BufRef ib = P.bufrefs[(size_t)inst * P.nbuf + P.in_buf];
+            const BufRef ob = P.bufrefs[(size_t)inst * P.nbuf + P.out_buf];
+            kind = ib.dtype == SIGOPS_F64 ? 1 : 2;
+            if (kind == 1) src = reinterpret_cast<const double*>(ib.ptr) + (int64_t)c * ib.ld + p0;
+            if (ob.dtype == SIGOPS_F64 && ((((uintptr_t)ob.ptr) | (uintptr_t)(ob.ld * 8)) & 15) == 0)
+                dstp = reinterpret_cast<double*>(ob.ptr) + (int64_t)c * ob.ld;
+        }
+        s_src[tid] = src;
+        s_rowkind[tid] = kind;
+        s_dst[tid] = dstp;
+        s_inst[tid] = inst_;
+        s_chan[tid] = c_;
+    }
+    // positions [jlo, jhi) of the tile exist in the signal; the rest is zero padding / history
+    const int ncopy = npos + 1;
+    const int jlo = p0 < 0 ? (int)(-p0 < ncopy ? -p0 : ncopy) : 0;
+    const int64_t avail = P.in_len - p0;
+    const int jhi = avail < 0 ? 0 : (avail < ncopy ? (int)avail : ncopy);
+    __syncthreads();
+
+    // ---- 1. start the window copy: rows x positions, lanes along positions
+    for (int r = warp; r < RB; r += kFirWarps) {
+        double* dst = xs + (size_t)r * P.xpitch;
+        const int kind = s_rowkind[r];
+        if (kind == 1) {
+            const double* src = s_src[r];
+            for (int j = lane; j < ncopy; j += 32) {
+                const bool ok = j >= jlo && j < jhi;
+                cp_async8(dst + j, src + (ok ? j : jlo), ok);
+            }
+        } else if (kind == 2) {
+            const int64_t row = row0 + r;
+            const int64_t inst = row / P.nch;
+            const int c = (int)(row - inst * P.nch);
+            const BufRef ib = P.bufrefs[(size_t)inst * P.nbuf + P.in_buf];
+            for (int j = lane; j < ncopy; j += 32)
+                dst[j] = (j >= jlo && j < jhi) ? load_elem(ib.ptr, ib.dtype, (int64_t)c * ib.ld + p0 + j) : 0.0;
+        } else {
+            for (int j = lane; j < ncopy; j += 32) dst[j] = 0.0;
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    // ---- 2. merged taps while the copies fly: 4 threads per output
+    for (int i = tid; i < P.epi_prog_len; i += kFirThreads) sprog_epi[i] = P.instrs[P.epi_prog_start + i];
+    {
+        const int m = tid >> 2, sub = tid & 3;
+        const int ws = (int)(P.xi0[m0 + m] - P.tapsper + 1 - p0);     // >= 0
+        if (sub == 0) s_ws[m] = ws;
+        double* hrow = hm + (size_t)m * P.tpad;
+        const int base = P.hbase + (ws & 1);                          // tap t lives at hrow[base + t]
+        for (int i = sub; i < P.tpad; i += 4)
+            if (i < base || i >= base + P.tapsper) hrow[i] = 0.0;
+        if (m0 + m < P.n_out) {
             const double acc = P.phi[m0 + m];
             const double fl = floor(acc);
-            const int64_t ph = (int64_t)fl - 1;
-            h = P.pfb[ph * P.tapsper + t];
-            if (P.dpfb) h = fma(acc - fl, P.dpfb[ph * P.tapsper + t], h);
-        }
-        hm[i] = h;
-    }
-    __syncthreads();
-
-    // ---- stage the input window, transposed to [position][row]
-    const int64_t p0 = s_xi0[0] - P.tapsper + 1;
-    const int npos = (int)(s_xi0[kFirT - 1] - p0 + 1);
-    for (int r = warp; r < kFirRB; r += kFirWarps) {
-        const int64_t row = row0 + r;
-        const bool live = row < P.nrows;
-        BufRef ib{};
-        int c = 0;
-        if (live) {
-            const int64_t inst = row / P.nch;
-            c = (int)(row % P.nch);
-            ib = P.bufrefs[(size_t)inst * P.nbuf + P.in_buf];
-        }
-        for (int j = lane; j < npos; j += 32) {
-            const int64_t p = p0 + j;
-            double v = 0.0;
-            if (live && p >= 0 && p < P.in_len) v = load_elem(ib.ptr, ib.dtype, (int64_t)c * ib.ld + p);
-            xs[(size_t)j * kFirRowPitch + r] = v;
+            const double alpha = acc - fl;
+            const double* pf = P.pfb + ((int64_t)fl - 1) * P.tapsper;
+            const double* dpf = P.dpfb ? P.dpfb + ((int64_t)fl - 1) * P.tapsper : nullptr;
+            for (int t = sub; t < P.tapsper; t += 4) {
+                double h = pf[t];
+                if (dpf) h = fma(alpha, dpf[t], h);
+                hrow[base + t] = h;
+            }
+        } else {
+            for (int t = sub; t < P.tapsper; t += 4) hrow[base + t] = 0.0;
         }
     }
+    cp_async_wait_all();
     __syncthreads();
 
-    // ---- register-tiled dot products: 8 outputs x 4 rows per thread
-    double acc[kFirR][kFirG];
+    // ---- 3. register-tiled dot products: 8 outputs x G rows per thread, two positions per step
+    double acc[kFirR][G];
 #pragma unroll
     for (int r = 0; r < kFirR; ++r)
 #pragma unroll
-        for (int g = 0; g < kFirG; ++g) acc[r][g] = 0.0;
+        for (int g = 0; g < G; ++g) acc[r][g] = 0.0;
     {
         const int mw = warp * kFirR;
-        const int64_t xw0 = s_xi0[mw];
+        const int qs = s_ws[mw] & ~1;                                 // first (even) position of the group
+        const int qe = s_ws[mw + kFirR - 1] + P.tapsper;              // one past the last position
+        // one tap-row pointer per output (index arithmetic hoisted out of the loop)
         const double* hp[kFirR];
 #pragma unroll
-        for (int r = 0; r < kFirR; ++r)
-            hp[r] = hm + (size_t)(mw + r) * P.tpad + P.dpad - (int)(s_xi0[mw + r] - xw0);
-        const int jn = P.tapsper + (int)(s_xi0[mw + kFirR - 1] - xw0);
-        const double* xp = xs + (size_t)(xw0 - P.tapsper + 1 - p0) * kFirRowPitch + lane;
-        for (int j = 0; j < jn; ++j) {
-            double xv[kFirG];
+        for (int r = 0; r < kFirR; ++r) {
+            const int ws = s_ws[mw + r];
+            hp[r] = hm + (mw + r) * P.tpad + P.hbase + (ws & 1) + (qs - ws);
+        }
+        const double* xrow[G];
 #pragma unroll
-            for (int g = 0; g < kFirG; ++g) xv[g] = xp[(size_t)j * kFirRowPitch + 32 * g];
+        for (int g = 0; g < G; ++g) xrow[g] = xs + (lane + 32 * g) * P.xpitch + qs;
+        const int npair = (qe - qs + 1) >> 1;
+        for (int k = 0; k < npair; ++k) {
+            double2 xv[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                xv[g] = *reinterpret_cast<const double2*>(xrow[g]);
+                xrow[g] += 2;
+            }
 #pragma unroll
             for (int r = 0; r < kFirR; ++r) {
-                const double hv = hp[r][j];
+                const double2 hv = *reinterpret_cast<const double2*>(hp[r]);
+                hp[r] += 2;
 #pragma unroll
-                for (int g = 0; g < kFirG; ++g) acc[r][g] = fma(hv, xv[g], acc[r][g]);
+                for (int g = 0; g < G; ++g) {
+                    acc[r][g] = fma(hv.x, xv[g].x, acc[r][g]);
+                    acc[r][g] = fma(hv.y, xv[g].y, acc[r][g]);
+                }
             }
         }
     }
     __syncthreads();
 
-    // ---- stage results as ys[output][row], then store rows coalesced along time
+    // ---- 4. stage results [row][output] (reusing the window tile), then coalesced row stores
     double* ys = xs;
 #pragma unroll
-    for (int r = 0; r < kFirR; ++r)
+    for (int g = 0; g < G; ++g) {
+        double* yr = ys + (size_t)(lane + 32 * g) * kFirYPitch + warp * kFirR;
 #pragma unroll
-        for (int g = 0; g < kFirG; ++g)
-            ys[(size_t)(warp * kFirR + r) * kFirRowPitch + lane + 32 * g] = acc[r][g];
+        for (int r = 0; r < kFirR; r += 2) *reinterpret_cast<double2*>(yr + r) = make_double2(acc[r][g], acc[r + 1][g]);
+    }
     __syncthreads();
 
-    for (int r = warp; r < kFirRB; r += kFirWarps) {
-        const int64_t row = row0 + r;
-        if (row >= P.nrows) break;
-        const int64_t inst = row / P.nch;
-        const int c = (int)(row % P.nch);
-        const BufRef* bufs = P.bufrefs + (size_t)inst * P.nbuf;
-        Env env{bufs, P.scalars + (size_t)inst * P.nscalars};
-        const BufRef ob = bufs[P.out_buf];
-        double y[2], o[2];
-        y[0] = ys[(size_t)lane * kFirRowPitch + r];
-        y[1] = ys[(size_t)(lane + 32) * kFirRowPitch + r];
+    for (int r = warp; r < RB; r += kFirWarps) {
+        if (s_rowkind[r] == 0) break;
+        const int inst = s_inst[r], c = s_chan[r];
+        const double2 yv = *reinterpret_cast<const double2*>(ys + (size_t)r * kFirYPitch + 2 * lane);
+        const int64_t m = m0 + 2 * lane;
+        double o0 = yv.x, o1 = yv.y;
         if (P.epi_prog_len > 0) {
+            const BufRef* bufs = P.bufrefs + (size_t)inst * P.nbuf;
+            Env env{bufs, P.scalars + (size_t)inst * P.nscalars};
             for (int i = lane; i < P.epi_prog_len; i += 32) {
                 const sigops_instr& I = sprog_epi[i];
                 double v = 0.0;
@@ -168,20 +236,21 @@ k_fir(const __grid_constant__ FirParams P) {
                 lc_epi[warp][i] = v;
             }
             __syncwarp();
-            eval_program<2>(sprog_epi, lc_epi[warp], P.epi_prog_len, env, m0 + lane, 32, c, y, o,
-                            stack + threadIdx.x, kFirThreads);
+            const double y[2] = {yv.x, yv.y};
+            double o[2];
+            eval_program<2>(sprog_epi, lc_epi[warp], P.epi_prog_len, env, m, 1, c, y, o, stack + tid, kFirThreads);
+            o0 = o[0]; o1 = o[1];
             __syncwarp();
-        } else {
-            o[0] = y[0]; o[1] = y[1];
         }
         double ss = 0.0;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int64_t m = m0 + lane + 32 * j;
-            if (m < P.n_out) {
-                const double w = store_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + m, o[j]);
-                ss += w * w;
-            }
+        double* dstp = s_dst[r];
+        if (dstp && m + 1 < P.n_out) {
+            *reinterpret_cast<double2*>(dstp + m) = make_double2(o0, o1);
+            ss = fma(o0, o0, o1 * o1);
+        } else {
+            const BufRef ob = P.bufrefs[(size_t)inst * P.nbuf + P.out_buf];
+            if (m < P.n_out) { const double w = store_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + m, o0); ss = fma(w, w, ss); }
+            if (m + 1 < P.n_out) { const double w = store_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + m + 1, o1); ss = fma(w, w, ss); }
         }
         if (P.sumsq_slot >= 0) {
             ss = warp_sum(ss);

@@ -23,10 +23,11 @@
 
 namespace sigops {
 
-constexpr int kTmaWarps = 6;
+constexpr int kTmaWarps = 8;
 constexpr int kTmaThreads = kTmaWarps * 32;
-constexpr int kStageCols = 64;                 // frames per stage (512 B)
-constexpr int kStagePitch = kStageCols + 2;    // doubles: 528-B rows keep 16-B alignment and make
+constexpr int kStageCols = 48;                 // frames per stage (384 B)
+static_assert(kStageCols % 16 == 0, "stage = whole 16-frame register blocks");
+constexpr int kStagePitch = kStageCols + 2;    // doubles: rows keep 16-B alignment; (cols+2)*2 = 4 mod 32 words makes
                                                // lane=row 128-bit accesses bank-conflict free
 constexpr int kStageBytes = kStageCols * 8;
 
@@ -202,9 +203,8 @@ k_iir_tma(const __grid_constant__ IirTmaParams Q) {
             bulk_wait_read_all();
             issue_load(h + 1);
         }
-        s4 += cascade16<M, MODE == IIR_FIX, UNITB>(f, buf + 16, P.gain, sc);
-        s4 += cascade16<M, MODE == IIR_FIX, UNITB>(f, buf + 32, P.gain, sc);
-        s4 += cascade16<M, MODE == IIR_FIX, UNITB>(f, buf + 48, P.gain, sc);
+#pragma unroll
+        for (int q = 16; q < kStageCols; q += 16) s4 += cascade16<M, MODE == IIR_FIX, UNITB>(f, buf + q, P.gain, sc);
         const int64_t rem = work - off;
         if (off < skip_frames) {
             // warm-up stage: outputs are not part of this chunk (pre is a multiple of the stage)

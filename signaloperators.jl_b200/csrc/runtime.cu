@@ -370,13 +370,22 @@ void derive_iir(sigops_plan& p, StageRT& s, int idx) {
 
 constexpr size_t kFirSmemLimit = 200 * 1024;
 
-// dynamic shared memory of k_fir<G>: merged taps + transposed window (reused for the
-// output tile) + the interpreter's spill stack
-size_t fir_smem_bytes(const FirDerived& f, int tapsper, int G, int max_stack) {
-    const size_t pitch = 32 * G + 1;
-    return ((size_t)kFirT * (tapsper + 2 * f.dpad) + (size_t)std::max(f.pmax, kFirT) * pitch +
-            (size_t)max_stack * 2 * kFirThreads) * sizeof(double);
+// k_fir<G> geometry: merged-tap rows, window pitch and dynamic shared memory
+struct FirGeom {
+    int hbase, tpad, xpitch;
+    size_t smem;
+};
+FirGeom fir_geometry(const FirDerived& f, int tapsper, int G, int max_stack) {
+    FirGeom g;
+    g.hbase = (f.dpad + 2) & ~1;                                   // even, >= dmax + 1
+    g.tpad = (g.hbase + tapsper + f.dpad + 5) & ~1;
+    const int need = f.pmax + 3;                                   // positions of a tile (+ even start, + pair tail)
+    g.xpitch = need + ((2 - need % 16) + 16) % 16;                 // = 2 mod 16
+    const size_t xrows = (size_t)std::max(g.xpitch, kFirYPitch);
+    g.smem = ((size_t)kFirT * g.tpad + (size_t)32 * G * xrows + (size_t)max_stack * 2 * kFirThreads) * sizeof(double);
+    return g;
 }
+size_t fir_smem_bytes(const FirDerived& f, int tapsper, int G, int max_stack) { return fir_geometry(f, tapsper, G, max_stack).smem; }
 
 void derive_fir(sigops_plan& p, StageRT& s, int idx) {
     const sigops_stage& st = s.st;
@@ -904,15 +913,17 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
             P.in_buf = s.fir.in_buf; P.in_len = s.fir.in_len;
             P.epi_prog_start = g.epi_prog_start; P.epi_prog_len = g.epi_prog_len;
             P.nch = g.nchannels; P.nrows = rows; P.n_out = g.n_out;
-            P.tapsper = g.taps_per_phase; P.dpad = s.fir.dpad; P.tpad = g.taps_per_phase + 2 * s.fir.dpad;
-            P.pmax = s.fir.pmax;
+            P.tapsper = g.taps_per_phase;
             P.pfb = pd.blob + p.tables[g.pfb_table].offset;
             P.dpfb = g.dpfb_table >= 0 ? pd.blob + p.tables[g.dpfb_table].offset : nullptr;
             P.xi0 = pd.xi0[si]; P.phi = pd.phi[si];
             // rows per thread: as many as fit in shared memory, but no more than the batch can fill
             int G = 4;
+            if (const char* e = getenv("SIGOPS_FIR_G")) G = std::max(1, std::min(4, atoi(e)));
             while (G > 1 && (fir_smem_bytes(s.fir, g.taps_per_phase, G, p.max_stack) > kFirSmemLimit || rows <= 16 * G)) G >>= 1;
-            const size_t smem = fir_smem_bytes(s.fir, g.taps_per_phase, G, p.max_stack);
+            const FirGeom geo = fir_geometry(s.fir, g.taps_per_phase, G, p.max_stack);
+            P.hbase = geo.hbase; P.tpad = geo.tpad; P.xpitch = geo.xpitch;
+            const size_t smem = geo.smem;
             const int64_t tiles = (g.n_out + kFirT - 1) / kFirT;
             const int64_t groups = (rows + 32 * G - 1) / (32 * G);
             if (groups > 65535) fail(SIGOPS_ERR_UNSUPPORTED, "FIR stage over more than %d rows per wave", 65535 * 32 * G);
