@@ -54,12 +54,17 @@ struct FirParams {
     int tapsper;
     int hbase;                 // even, > max window shift inside a group of 8 outputs
     int tpad;                  // doubles per merged-tap row (even)
-    int xpitch;                // doubles per window row, = 2 mod 16, >= max positions of a tile + 2
+    int xpitch;                // doubles per window row, = 2 mod 4, >= max positions of a tile + 2
     const double* pfb;         // [nphases][tapsper]
     const double* dpfb;        // or nullptr
     const int64_t* xi0;        // [ceil(n_out/T)*T], tail repeats the last entry
     const double* phi;
 };
+
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src, int src_bytes) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
 
 template <int G>
 __global__ void __launch_bounds__(kFirThreads)
@@ -122,9 +127,21 @@ k_fir(const __grid_constant__ FirParams P) {
         const int kind = s_rowkind[r];
         if (kind == 1) {
             const double* src = s_src[r];
-            for (int j = lane; j < ncopy; j += 32) {
-                const bool ok = j >= jlo && j < jhi;
-                cp_async8(dst + j, src + (ok ? j : jlo), ok);
+            if ((((uintptr_t)src) & 15) == 0) {
+                // two positions per lane; a pair straddling the end of the signal reads 8 bytes
+                for (int j = 2 * lane; j < ncopy; j += 64) {
+                    const int nb = (j >= jlo && j < jhi) ? ((j + 1 < jhi) ? 16 : 8) : 0;
+                    if (j + 1 >= jlo && j < jlo) {            // pair straddling the start: element-wise
+                        cp_async8(dst + j, src + jlo, false);
+                        cp_async8(dst + j + 1, src + j + 1, j + 1 < jhi);
+                    } else
+                        cp_async16(dst + j, src + (nb ? j : jlo), nb);
+                }
+            } else {
+                for (int j = lane; j < ncopy; j += 32) {
+                    const bool ok = j >= jlo && j < jhi;
+                    cp_async8(dst + j, src + (ok ? j : jlo), ok);
+                }
             }
         } else if (kind == 2) {
             const int64_t row = row0 + r;
@@ -219,39 +236,71 @@ k_fir(const __grid_constant__ FirParams P) {
     }
     __syncthreads();
 
+    const bool plain_store = P.epi_prog_len == 0;
+    if (plain_store) {
+        // fast path: lanes 0-15 take row r, lanes 16-31 row r+1; each store instruction
+        // writes one contiguous 256-byte span per row (outputs 2l..2l+1, then 32+2l..33+2l)
+        const int half = lane >> 4, l16 = lane & 15;
+        const int64_t ma = m0 + 2 * l16, mb = ma + 32;
+        for (int r = 2 * warp + half; r < RB; r += 2 * kFirWarps) {
+            if (s_rowkind[r] == 0) continue;
+            const double* yp = ys + r * kFirYPitch + 2 * l16;
+            const double2 a = *reinterpret_cast<const double2*>(yp);
+            const double2 b2 = *reinterpret_cast<const double2*>(yp + 32);
+            double* dstp = s_dst[r];
+            double ss = 0.0;
+            if (dstp && mb + 1 < P.n_out) {
+                *reinterpret_cast<double2*>(dstp + ma) = a;
+                *reinterpret_cast<double2*>(dstp + mb) = b2;
+                ss = fma(a.x, a.x, fma(a.y, a.y, fma(b2.x, b2.x, b2.y * b2.y)));
+            } else {
+                const int inst = s_inst[r], c = s_chan[r];
+                const BufRef ob = P.bufrefs[(size_t)inst * P.nbuf + P.out_buf];
+                const double o[4] = {a.x, a.y, b2.x, b2.y};
+                const int64_t mm[4] = {ma, ma + 1, mb, mb + 1};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (mm[j] < P.n_out) {
+                        const double w = store_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + mm[j], o[j]);
+                        ss = fma(w, w, ss);
+                    }
+            }
+            if (P.sumsq_slot >= 0) {
+                // reduce over the 16 lanes of this row
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                if (l16 == 0) atomicAdd(P.scalars + (size_t)s_inst[r] * P.nscalars + P.sumsq_slot, ss);
+            }
+        }
+        return;
+    }
     for (int r = warp; r < RB; r += kFirWarps) {
         if (s_rowkind[r] == 0) break;
         const int inst = s_inst[r], c = s_chan[r];
         const double2 yv = *reinterpret_cast<const double2*>(ys + (size_t)r * kFirYPitch + 2 * lane);
         const int64_t m = m0 + 2 * lane;
-        double o0 = yv.x, o1 = yv.y;
-        if (P.epi_prog_len > 0) {
-            const BufRef* bufs = P.bufrefs + (size_t)inst * P.nbuf;
-            Env env{bufs, P.scalars + (size_t)inst * P.nscalars};
-            for (int i = lane; i < P.epi_prog_len; i += 32) {
-                const sigops_instr& I = sprog_epi[i];
-                double v = 0.0;
-                if (I.leaf == SIGOPS_LEAF_CONST) v = I.d0;
-                else if (I.leaf == SIGOPS_LEAF_RMS) v = sqrt(env.scalars[I.buf] / I.d0);
-                lc_epi[warp][i] = v;
-            }
-            __syncwarp();
-            const double y[2] = {yv.x, yv.y};
-            double o[2];
-            eval_program<2>(sprog_epi, lc_epi[warp], P.epi_prog_len, env, m, 1, c, y, o, stack + tid, kFirThreads);
-            o0 = o[0]; o1 = o[1];
-            __syncwarp();
+        const BufRef* bufs = P.bufrefs + (size_t)inst * P.nbuf;
+        Env env{bufs, P.scalars + (size_t)inst * P.nscalars};
+        for (int i = lane; i < P.epi_prog_len; i += 32) {
+            const sigops_instr& I = sprog_epi[i];
+            double v = 0.0;
+            if (I.leaf == SIGOPS_LEAF_CONST) v = I.d0;
+            else if (I.leaf == SIGOPS_LEAF_RMS) v = sqrt(env.scalars[I.buf] / I.d0);
+            lc_epi[warp][i] = v;
         }
+        __syncwarp();
+        const double y[2] = {yv.x, yv.y};
+        double o[2];
+        eval_program<2>(sprog_epi, lc_epi[warp], P.epi_prog_len, env, m, 1, c, y, o, stack + tid, kFirThreads);
+        __syncwarp();
         double ss = 0.0;
-        double* dstp = s_dst[r];
-        if (dstp && m + 1 < P.n_out) {
-            *reinterpret_cast<double2*>(dstp + m) = make_double2(o0, o1);
-            ss = fma(o0, o0, o1 * o1);
-        } else {
-            const BufRef ob = P.bufrefs[(size_t)inst * P.nbuf + P.out_buf];
-            if (m < P.n_out) { const double w = store_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + m, o0); ss = fma(w, w, ss); }
-            if (m + 1 < P.n_out) { const double w = store_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + m + 1, o1); ss = fma(w, w, ss); }
-        }
+        const BufRef ob = bufs[P.out_buf];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (m + j < P.n_out) {
+                const double w = store_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + m + j, o[j]);
+                ss = fma(w, w, ss);
+            }
         if (P.sumsq_slot >= 0) {
             ss = warp_sum(ss);
             if (lane == 0) atomicAdd(P.scalars + (size_t)inst * P.nscalars + P.sumsq_slot, ss);

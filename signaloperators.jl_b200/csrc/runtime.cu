@@ -380,7 +380,7 @@ FirGeom fir_geometry(const FirDerived& f, int tapsper, int G, int max_stack) {
     g.hbase = (f.dpad + 2) & ~1;                                   // even, >= dmax + 1
     g.tpad = (g.hbase + tapsper + f.dpad + 5) & ~1;
     const int need = f.pmax + 3;                                   // positions of a tile (+ even start, + pair tail)
-    g.xpitch = need + ((2 - need % 16) + 16) % 16;                 // = 2 mod 16
+    g.xpitch = need + ((2 - need % 4) + 4) % 4;                    // = 2 mod 4: lane=row 128-bit reads conflict free
     const size_t xrows = (size_t)std::max(g.xpitch, kFirYPitch);
     g.smem = ((size_t)kFirT * g.tpad + (size_t)32 * G * xrows + (size_t)max_stack * 2 * kFirThreads) * sizeof(double);
     return g;
@@ -530,6 +530,10 @@ void parse_plan(sigops_plan& p, const void* bytes, size_t nbytes) {
             if (g.in_prog_len < 1) fail(SIGOPS_ERR_INVALID, "%s: missing input program", what);
             p.max_stack = std::max(p.max_stack, program_stack_depth(p, g.in_prog_start, g.in_prog_len, false, what));
             p.max_stack = std::max(p.max_stack, program_stack_depth(p, g.epi_prog_start, g.epi_prog_len, true, what));
+            // an epilogue that is just "LOAD the stage value" (a fused plain copy) is no epilogue
+            if (g.epi_prog_len == 1 && p.instrs[g.epi_prog_start].op == SIGOPS_OP_LOAD &&
+                p.instrs[g.epi_prog_start].leaf == SIGOPS_LEAF_STAGE)
+                s.st.epi_prog_len = 0;
             if (g.kind == SIGOPS_STAGE_IIR) derive_iir(p, s, (int)i);
             else derive_fir(p, s, (int)i);
         } else
