@@ -33,11 +33,10 @@
 
 namespace sigops {
 
-constexpr int kFirWarps = 8;
-constexpr int kFirThreads = kFirWarps * 32;
 constexpr int kFirR = 8;                    // outputs per thread
-constexpr int kFirT = kFirWarps * kFirR;    // outputs per tile (64)
-constexpr int kFirYPitch = kFirT + 2;       // doubles; = 2 mod 16 keeps lane=row 128-bit stores conflict free
+constexpr int kFirMaxWarps = 8;
+// W warps per block: tile of T = 8*W outputs (W = 8: 64 outputs, W = 4: 32 outputs — the smaller
+// tile lets two 128-row blocks share an SM so one block's copies overlap the other's FMAs)
 
 struct FirParams {
     const sigops_instr* instrs;
@@ -66,12 +65,14 @@ __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
 
-template <int G>
-__global__ void __launch_bounds__(kFirThreads)
+template <int G, int W>
+__global__ void __launch_bounds__(W * 32)
 k_fir(const __grid_constant__ FirParams P) {
     constexpr int RB = 32 * G;
+    constexpr int kFirWarps = W, kFirThreads = W * 32, kFirT = W * kFirR;
+    constexpr int kFirYPitch = kFirT + 2;       // doubles; = 2 mod 4 keeps lane=row 128-bit stores conflict free
     __shared__ sigops_instr sprog_epi[SIGOPS_MAX_PROG];
-    __shared__ double lc_epi[kFirWarps][SIGOPS_MAX_PROG];
+    __shared__ double lc_epi[W][SIGOPS_MAX_PROG];
     __shared__ int s_ws[kFirT];                           // window start of output m relative to the tile
     extern __shared__ __align__(16) double smem[];
     double* hm = smem;                                    // [T][tpad]
@@ -82,10 +83,28 @@ k_fir(const __grid_constant__ FirParams P) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t m0 = (int64_t)blockIdx.x * kFirT;
     const int64_t row0 = (int64_t)blockIdx.y * RB;
+    // Everything the block needs from global memory before it can start copying is requested
+    // up front, so the dependent-load chain at block start is one memory latency long:
+    // my output's index/phase (4 threads per output), the tile's first/last index, my row's buffers.
+    const int my_m = tid >> 2;
+    const int64_t my_xi0 = __ldg(P.xi0 + m0 + my_m);
+    const double my_phi = __ldg(P.phi + m0 + my_m);
+    const int64_t xi_first = __ldg(P.xi0 + m0), xi_last = __ldg(P.xi0 + m0 + kFirT - 1);
+    BufRef my_ib{}, my_ob{};
+    int my_inst = 0, my_c = 0;
+    const bool my_row_live = tid < RB && row0 + tid < P.nrows;
+    if (my_row_live) {
+        const int64_t row = row0 + tid;
+        const int64_t inst = row / P.nch;
+        my_inst = (int)inst;
+        my_c = (int)(row - inst * P.nch);
+        my_ib = P.bufrefs[(size_t)inst * P.nbuf + P.in_buf];
+        my_ob = P.bufrefs[(size_t)inst * P.nbuf + P.out_buf];
+    }
     // tile window: even start so that position pairs stay 16-byte aligned
-    const int64_t p_first = P.xi0[m0] - P.tapsper + 1;
+    const int64_t p_first = xi_first - P.tapsper + 1;
     const int64_t p0 = p_first & ~int64_t(1);
-    const int npos = (int)(P.xi0[m0 + kFirT - 1] - p0 + 1);
+    const int npos = (int)(xi_last - p0 + 1);
 
     // ---- 0. per-row addressing, once per block (one thread per row)
     __shared__ const double* s_src[32 * 4];     // row base + p0 for Float64 rows, else nullptr
@@ -93,26 +112,20 @@ k_fir(const __grid_constant__ FirParams P) {
     __shared__ double* s_dst[32 * 4];           // output row base when it takes aligned Float64 pair stores
     __shared__ int s_inst[32 * 4], s_chan[32 * 4];
     if (tid < RB) {
-        const int64_t row = row0 + tid;
         const double* src = nullptr;
         double* dstp = nullptr;
-        int kind = 0, inst_ = 0, c_ = 0;
-        if (row < P.nrows) {
-            const int64_t inst = row / P.nch;
-            const int c = (int)(row - inst * P.nch);
-            inst_ = (int)inst; c_ = c;
-            const BufRef ib = P.bufrefs[(size_t)inst * P.nbuf + P.in_buf];
-            const BufRef ob = P.bufrefs[(size_t)inst * P.nbuf + P.out_buf];
-            kind = ib.dtype == SIGOPS_F64 ? 1 : 2;
-            if (kind == 1) src = reinterpret_cast<const double*>(ib.ptr) + (int64_t)c * ib.ld + p0;
-            if (ob.dtype == SIGOPS_F64 && ((((uintptr_t)ob.ptr) | (uintptr_t)(ob.ld * 8)) & 15) == 0)
-                dstp = reinterpret_cast<double*>(ob.ptr) + (int64_t)c * ob.ld;
+        int kind = 0;
+        if (my_row_live) {
+            kind = my_ib.dtype == SIGOPS_F64 ? 1 : 2;
+            if (kind == 1) src = reinterpret_cast<const double*>(my_ib.ptr) + (int64_t)my_c * my_ib.ld + p0;
+            if (my_ob.dtype == SIGOPS_F64 && ((((uintptr_t)my_ob.ptr) | (uintptr_t)(my_ob.ld * 8)) & 15) == 0)
+                dstp = reinterpret_cast<double*>(my_ob.ptr) + (int64_t)my_c * my_ob.ld;
         }
         s_src[tid] = src;
         s_rowkind[tid] = kind;
         s_dst[tid] = dstp;
-        s_inst[tid] = inst_;
-        s_chan[tid] = c_;
+        s_inst[tid] = my_inst;
+        s_chan[tid] = my_c;
     }
     // positions [jlo, jhi) of the tile exist in the signal; the rest is zero padding / history
     const int ncopy = npos + 1;
@@ -154,27 +167,28 @@ k_fir(const __grid_constant__ FirParams P) {
             for (int j = lane; j < ncopy; j += 32) dst[j] = 0.0;
         }
     }
+    for (int i = tid; i < RB * 8; i += kFirThreads) xs[(size_t)(i >> 3) * P.xpitch + ncopy + (i & 7)] = 0.0;
     asm volatile("cp.async.commit_group;" ::: "memory");
 
     // ---- 2. merged taps while the copies fly: 4 threads per output
     for (int i = tid; i < P.epi_prog_len; i += kFirThreads) sprog_epi[i] = P.instrs[P.epi_prog_start + i];
     {
-        const int m = tid >> 2, sub = tid & 3;
-        const int ws = (int)(P.xi0[m0 + m] - P.tapsper + 1 - p0);     // >= 0
+        const int m = my_m, sub = tid & 3;
+        const int ws = (int)(my_xi0 - P.tapsper + 1 - p0);            // >= 0
         if (sub == 0) s_ws[m] = ws;
         double* hrow = hm + (size_t)m * P.tpad;
         const int base = P.hbase + (ws & 1);                          // tap t lives at hrow[base + t]
         for (int i = sub; i < P.tpad; i += 4)
             if (i < base || i >= base + P.tapsper) hrow[i] = 0.0;
         if (m0 + m < P.n_out) {
-            const double acc = P.phi[m0 + m];
+            const double acc = my_phi;
             const double fl = floor(acc);
             const double alpha = acc - fl;
             const double* pf = P.pfb + ((int64_t)fl - 1) * P.tapsper;
             const double* dpf = P.dpfb ? P.dpfb + ((int64_t)fl - 1) * P.tapsper : nullptr;
             for (int t = sub; t < P.tapsper; t += 4) {
-                double h = pf[t];
-                if (dpf) h = fma(alpha, dpf[t], h);
+                double h = __ldg(pf + t);
+                if (dpf) h = fma(alpha, __ldg(dpf + t), h);
                 hrow[base + t] = h;
             }
         } else {
@@ -204,24 +218,31 @@ k_fir(const __grid_constant__ FirParams P) {
         const double* xrow[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) xrow[g] = xs + (lane + 32 * g) * P.xpitch + qs;
-        const int npair = (qe - qs + 1) >> 1;
-        for (int k = 0; k < npair; ++k) {
-            double2 xv[G];
+        // four position pairs per iteration (immediate offsets, one pointer bump each); the
+        // tail reads zero taps / zeroed slack, so no remainder loop is needed
+        const int nquad = (qe - qs + 7) >> 3;
+        for (int k = 0; k < nquad; ++k) {
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                xv[g] = *reinterpret_cast<const double2*>(xrow[g]);
-                xrow[g] += 2;
-            }
+            for (int u = 0; u < 4; ++u) {
+                double2 xv[G];
 #pragma unroll
-            for (int r = 0; r < kFirR; ++r) {
-                const double2 hv = *reinterpret_cast<const double2*>(hp[r]);
-                hp[r] += 2;
+                for (int g = 0; g < G; ++g) xv[g] = *reinterpret_cast<const double2*>(xrow[g] + 2 * u);
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    acc[r][g] = fma(hv.x, xv[g].x, acc[r][g]);
-                    acc[r][g] = fma(hv.y, xv[g].y, acc[r][g]);
+                for (int r = 0; r < kFirR; ++r) {
+                    // two 64-bit broadcast loads: a warp-uniform 128-bit load costs four shared-memory
+                    // wavefronts (one per quarter warp), a uniform 64-bit load only one
+                    const double h0 = hp[r][2 * u], h1 = hp[r][2 * u + 1];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        acc[r][g] = fma(h0, xv[g].x, acc[r][g]);
+                        acc[r][g] = fma(h1, xv[g].y, acc[r][g]);
+                    }
                 }
             }
+#pragma unroll
+            for (int g = 0; g < G; ++g) xrow[g] += 8;
+#pragma unroll
+            for (int r = 0; r < kFirR; ++r) hp[r] += 8;
         }
     }
     __syncthreads();
@@ -239,31 +260,27 @@ k_fir(const __grid_constant__ FirParams P) {
     const bool plain_store = P.epi_prog_len == 0;
     if (plain_store) {
         // fast path: lanes 0-15 take row r, lanes 16-31 row r+1; each store instruction
-        // writes one contiguous 256-byte span per row (outputs 2l..2l+1, then 32+2l..33+2l)
+        // writes one contiguous 256-byte span per row (outputs 32*q + 2l .. 2l+1)
         const int half = lane >> 4, l16 = lane & 15;
-        const int64_t ma = m0 + 2 * l16, mb = ma + 32;
+        constexpr int NQ = kFirT / 32;
         for (int r = 2 * warp + half; r < RB; r += 2 * kFirWarps) {
             if (s_rowkind[r] == 0) continue;
             const double* yp = ys + r * kFirYPitch + 2 * l16;
-            const double2 a = *reinterpret_cast<const double2*>(yp);
-            const double2 b2 = *reinterpret_cast<const double2*>(yp + 32);
             double* dstp = s_dst[r];
             double ss = 0.0;
-            if (dstp && mb + 1 < P.n_out) {
-                *reinterpret_cast<double2*>(dstp + ma) = a;
-                *reinterpret_cast<double2*>(dstp + mb) = b2;
-                ss = fma(a.x, a.x, fma(a.y, a.y, fma(b2.x, b2.x, b2.y * b2.y)));
-            } else {
-                const int inst = s_inst[r], c = s_chan[r];
-                const BufRef ob = P.bufrefs[(size_t)inst * P.nbuf + P.out_buf];
-                const double o[4] = {a.x, a.y, b2.x, b2.y};
-                const int64_t mm[4] = {ma, ma + 1, mb, mb + 1};
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (mm[j] < P.n_out) {
-                        const double w = store_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + mm[j], o[j]);
-                        ss = fma(w, w, ss);
-                    }
+            for (int q = 0; q < NQ; ++q) {
+                const double2 a = *reinterpret_cast<const double2*>(yp + 32 * q);
+                const int64_t m = m0 + 32 * q + 2 * l16;
+                if (dstp && m + 1 < P.n_out) {
+                    *reinterpret_cast<double2*>(dstp + m) = a;
+                    ss = fma(a.x, a.x, fma(a.y, a.y, ss));
+                } else {
+                    const int inst = s_inst[r], c = s_chan[r];
+                    const BufRef ob = P.bufrefs[(size_t)inst * P.nbuf + P.out_buf];
+                    if (m < P.n_out) { const double w = store_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + m, a.x); ss = fma(w, w, ss); }
+                    if (m + 1 < P.n_out) { const double w = store_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + m + 1, a.y); ss = fma(w, w, ss); }
+                }
             }
             if (P.sumsq_slot >= 0) {
                 // reduce over the 16 lanes of this row
@@ -277,7 +294,8 @@ k_fir(const __grid_constant__ FirParams P) {
     for (int r = warp; r < RB; r += kFirWarps) {
         if (s_rowkind[r] == 0) break;
         const int inst = s_inst[r], c = s_chan[r];
-        const double2 yv = *reinterpret_cast<const double2*>(ys + (size_t)r * kFirYPitch + 2 * lane);
+        const bool lane_on = 2 * lane < kFirT;
+        const double2 yv = lane_on ? *reinterpret_cast<const double2*>(ys + (size_t)r * kFirYPitch + 2 * lane) : make_double2(0.0, 0.0);
         const int64_t m = m0 + 2 * lane;
         const BufRef* bufs = P.bufrefs + (size_t)inst * P.nbuf;
         Env env{bufs, P.scalars + (size_t)inst * P.nscalars};
@@ -297,7 +315,7 @@ k_fir(const __grid_constant__ FirParams P) {
         const BufRef ob = bufs[P.out_buf];
 #pragma unroll
         for (int j = 0; j < 2; ++j)
-            if (m + j < P.n_out) {
+            if (lane_on && m + j < P.n_out) {
                 const double w = store_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + m + j, o[j]);
                 ss = fma(w, w, ss);
             }

@@ -177,7 +177,8 @@ struct IirDerived {
 struct FirDerived {
     std::vector<int64_t> xi0;
     std::vector<double> phi;
-    int dpad = 0, pmax = 0;
+    int dpad = 0, pmax = 0;      // window shift inside 8 outputs; positions of a 64-output tile
+    int pmax32 = 0;              // positions of a 32-output tile
     int in_buf = -1;
     int64_t in_len = 0;
 };
@@ -369,20 +370,22 @@ void derive_iir(sigops_plan& p, StageRT& s, int idx) {
 }
 
 constexpr size_t kFirSmemLimit = 200 * 1024;
+constexpr int kFirT = 64;     // table padding granularity (largest tile)
 
 // k_fir<G> geometry: merged-tap rows, window pitch and dynamic shared memory
 struct FirGeom {
     int hbase, tpad, xpitch;
     size_t smem;
 };
-FirGeom fir_geometry(const FirDerived& f, int tapsper, int G, int max_stack) {
+FirGeom fir_geometry(const FirDerived& f, int tapsper, int G, int max_stack, int W = 8) {
     FirGeom g;
+    const int T = 8 * W, ypitch = T + 2, pmax = W == 8 ? f.pmax : f.pmax32;
     g.hbase = (f.dpad + 2) & ~1;                                   // even, >= dmax + 1
-    g.tpad = (g.hbase + tapsper + f.dpad + 5) & ~1;
-    const int need = f.pmax + 3;                                   // positions of a tile (+ even start, + pair tail)
+    g.tpad = (g.hbase + tapsper + f.dpad + 5 + 8) & ~1;            // + 8: slack read by the 4-pair unrolled tail
+    const int need = pmax + 3 + 8;                               // positions of a tile (+ even start, pair tail, unroll slack)
     g.xpitch = need + ((2 - need % 4) + 4) % 4;                    // = 2 mod 4: lane=row 128-bit reads conflict free
-    const size_t xrows = (size_t)std::max(g.xpitch, kFirYPitch);
-    g.smem = ((size_t)kFirT * g.tpad + (size_t)32 * G * xrows + (size_t)max_stack * 2 * kFirThreads) * sizeof(double);
+    const size_t xrows = (size_t)std::max(g.xpitch, ypitch);
+    g.smem = ((size_t)T * g.tpad + (size_t)32 * G * xrows + (size_t)max_stack * 2 * W * 32) * sizeof(double);
     return g;
 }
 size_t fir_smem_bytes(const FirDerived& f, int tapsper, int G, int max_stack) { return fir_geometry(f, tapsper, G, max_stack).smem; }
@@ -459,8 +462,11 @@ void derive_fir(sigops_plan& p, StageRT& s, int idx) {
     int64_t dpad = 0, span = 0;
     for (int64_t m = 0; m + kFirR - 1 < padded; ++m) dpad = std::max(dpad, s.fir.xi0[m + kFirR - 1] - s.fir.xi0[m]);
     for (int64_t m = 0; m < padded; m += kFirT) span = std::max(span, s.fir.xi0[m + kFirT - 1] - s.fir.xi0[m]);
+    int64_t span32 = 0;
+    for (int64_t m = 0; m < padded; m += 32) span32 = std::max(span32, s.fir.xi0[m + 31] - s.fir.xi0[m]);
     s.fir.dpad = (int)dpad;
     s.fir.pmax = (int)(span + st.taps_per_phase);
+    s.fir.pmax32 = (int)(span32 + st.taps_per_phase);
     if (fir_smem_bytes(s.fir, st.taps_per_phase, 1, SIGOPS_MAX_STACK) > kFirSmemLimit)
         fail(SIGOPS_ERR_UNSUPPORTED, "%s: resampling ratio %g with %d taps/phase needs %zu bytes of shared memory per block",
              what, st.rate, st.taps_per_phase, fir_smem_bytes(s.fir, st.taps_per_phase, 1, SIGOPS_MAX_STACK));
@@ -925,23 +931,32 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
             int G = 4;
             if (const char* e = getenv("SIGOPS_FIR_G")) G = std::max(1, std::min(4, atoi(e)));
             while (G > 1 && (fir_smem_bytes(s.fir, g.taps_per_phase, G, p.max_stack) > kFirSmemLimit || rows <= 16 * G)) G >>= 1;
-            const FirGeom geo = fir_geometry(s.fir, g.taps_per_phase, G, p.max_stack);
+            // 32-output tiles when two such blocks fit on an SM (copies of one overlap FMAs of the other)
+            // (measured on B200, config 3: 64-output tiles 3.8 ms vs 32-output tiles 4.7 ms — the smaller
+            //  tile's extra halo and per-tile set-up cost more than the overlap buys; kept as a knob)
+            int W = 8;
+            if (const char* e = getenv("SIGOPS_FIR_W")) W = atoi(e) == 4 && G == 4 ? 4 : 8;
+            const FirGeom geo = fir_geometry(s.fir, g.taps_per_phase, G, p.max_stack, W);
             P.hbase = geo.hbase; P.tpad = geo.tpad; P.xpitch = geo.xpitch;
             const size_t smem = geo.smem;
-            const int64_t tiles = (g.n_out + kFirT - 1) / kFirT;
+            const int T = 8 * W;
+            const int64_t tiles = (g.n_out + T - 1) / T;
             const int64_t groups = (rows + 32 * G - 1) / (32 * G);
             if (groups > 65535) fail(SIGOPS_ERR_UNSUPPORTED, "FIR stage over more than %d rows per wave", 65535 * 32 * G);
             dim3 grid((unsigned)tiles, (unsigned)groups);
             add(KIND_FIR, [=](cudaStream_t st) {
-                if (G == 4) {
-                    ensure_dyn_smem(k_fir<4>, smem);
-                    k_fir<4><<<grid, kFirThreads, smem, st>>>(P);
+                if (G == 4 && W == 4) {
+                    ensure_dyn_smem(k_fir<4, 4>, smem);
+                    k_fir<4, 4><<<grid, 128, smem, st>>>(P);
+                } else if (G == 4) {
+                    ensure_dyn_smem(k_fir<4, 8>, smem);
+                    k_fir<4, 8><<<grid, 256, smem, st>>>(P);
                 } else if (G == 2) {
-                    ensure_dyn_smem(k_fir<2>, smem);
-                    k_fir<2><<<grid, kFirThreads, smem, st>>>(P);
+                    ensure_dyn_smem(k_fir<2, 8>, smem);
+                    k_fir<2, 8><<<grid, 256, smem, st>>>(P);
                 } else {
-                    ensure_dyn_smem(k_fir<1>, smem);
-                    k_fir<1><<<grid, kFirThreads, smem, st>>>(P);
+                    ensure_dyn_smem(k_fir<1, 8>, smem);
+                    k_fir<1, 8><<<grid, 256, smem, st>>>(P);
                 }
             });
         }
