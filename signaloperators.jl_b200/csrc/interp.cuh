@@ -115,19 +115,66 @@ __device__ __forceinline__ double leaf_value(const sigops_instr& I, const Env& e
     return 0.0;
 }
 
+
+// V frames of a sinusoidal generator, `nstride` apart: exact (reference formula,
+// src/functions.jl:53-60) for the first, angle addition for the rest.
+template <int V>
+__device__ __forceinline__ void gen_trig_values(const sigops_instr& I, double2 rot, int64_t k0, double* out) {
+    const double t = (double)k0 / I.d0;
+    double s, c;
+    if (I.flags & SIGOPS_FLAG_HAS_OMEGA) {
+        const double u = t * I.d1 + I.d2;
+        if (I.fn == SIGOPS_FN_SIN) sincospi(2.0 * u, &s, &c);
+        else sincos(6.283185307179586 * fmod(u, 1.0), &s, &c);
+    } else if (I.fn == SIGOPS_FN_SIN) {
+        sincospi(2.0 * (t + I.d2), &s, &c);
+    } else {
+        sincos(t + I.d2, &s, &c);
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        double v;
+        switch (I.fn) {
+            case SIGOPS_FN_SIN: v = s; break;
+            case SIGOPS_FN_COS: v = c; break;
+            case SIGOPS_FN_AFFINE_SIN: v = I.d3 * s + I.d4; break;
+            default: v = I.d3 * c + I.d4; break;
+        }
+        out[j] = v;
+        const double s2 = fma(s, rot.y, c * rot.x), c2 = fma(c, rot.y, -s * rot.x);
+        s = s2; c = c2;
+    }
+}
+
+__device__ __forceinline__ bool gen_is_trig(const sigops_instr& I) {
+    return I.fn == SIGOPS_FN_SIN || I.fn == SIGOPS_FN_COS || I.fn == SIGOPS_FN_AFFINE_SIN || I.fn == SIGOPS_FN_AFFINE_COS;
+}
+
 // Per-block preparation: copy the program to shared memory and fold the leaves
 // that do not depend on (n,c) (constants, Normpower divisors) into leafconst[].
+// For sinusoidal generators leafrot[] gets (sin, cos) of the phase advance between two
+// consecutive frames a thread evaluates (`nstride` frames apart): eval_program evaluates
+// the first frame with the reference's formula and reaches the next ones by angle
+// addition — 4 FMAs instead of a Float64 sin() per sample, exact to a few ulp.
 __device__ __forceinline__ void prepare_program(const sigops_instr* __restrict__ gprog, int len,
-                                                sigops_instr* sprog, double* leafconst,
-                                                const Env& env) {
+                                                sigops_instr* sprog, double* leafconst, double2* leafrot,
+                                                const Env& env, int64_t nstride) {
     for (int i = threadIdx.x; i < len; i += blockDim.x) {
         sigops_instr I = gprog[i];
         sprog[i] = I;
         double v = 0.0;
+        double2 rot = make_double2(0.0, 1.0);
         if (I.leaf == SIGOPS_LEAF_CONST) v = I.d0;
         // rms = sqrt(mean(x^2)) over the whole N x C matrix, src/filters.jl:304
         else if (I.leaf == SIGOPS_LEAF_RMS) v = sqrt(env.scalars[I.buf] / I.d0);
+        else if (I.leaf == SIGOPS_LEAF_GEN && gen_is_trig(I)) {
+            const double w = (I.flags & SIGOPS_FLAG_HAS_OMEGA) ? I.d1 : 1.0;     // cycles per second
+            double cyc = (double)nstride / I.d0 * w;                             // cycles per step
+            if (!(I.flags & SIGOPS_FLAG_HAS_OMEGA) && I.fn != SIGOPS_FN_SIN) cyc *= 0.15915494309189535;  // fn(t): radians
+            sincospi(2.0 * cyc, &rot.x, &rot.y);
+        }
         leafconst[i] = v;
+        leafrot[i] = rot;
     }
 }
 
@@ -140,27 +187,106 @@ __device__ __forceinline__ double binop(int op, double a, double b) {
     }
 }
 
-// Evaluate a program for V samples n[j] = n0 + j*nstride of channel c.
-// `stack` is this thread's spill area, laid out [depth][V] with stride
-// `sstride` doubles between consecutive slots (so neighbouring threads
-// interleave and stay bank-conflict free).
+// Evaluate a program for V samples n[j] = n0 + j*nstride of channel c (nstride must be
+// the stride prepare_program was given).  `stack` is this thread's spill area, laid out
+// [depth][V] with stride `sstride` doubles between consecutive slots (so neighbouring
+// threads interleave and stay bank-conflict free).
+// V frames of a buffer leaf, `nstride` apart.  The common case (Float64, every frame
+// inside the valid range) is V plain loads off one base pointer; everything else falls
+// back to the per-frame path (pads, other sample types).
+template <int V>
+__device__ __forceinline__ void buf_values(const sigops_instr& I, const Env& env, int64_t n0, int64_t nstride,
+                                           int c, double* out) {
+    const BufRef b = env.bufs[I.buf];
+    const int64_t idx0 = n0 + I.i0;
+    const int ch = c * I.c_mul + I.c_off;
+    if (b.dtype == SIGOPS_F64 && idx0 >= 0 && idx0 + (V - 1) * nstride < I.i1) {
+        const double* p = reinterpret_cast<const double*>(b.ptr) + (int64_t)ch * b.ld + idx0;
+#pragma unroll
+        for (int j = 0; j < V; ++j) out[j] = __ldg(p + j * nstride);
+        return;
+    }
+    const int pad = (I.flags >> 1) & 3;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        int64_t idx = idx0 + j * nstride;
+        bool use_pad = false;
+        if (idx < 0 || idx >= I.i1) {
+            if (pad == SIGOPS_PAD_CONST || idx < 0 || I.i1 <= 0) use_pad = true;
+            else if (pad == SIGOPS_PAD_CYCLE) idx = idx % I.i1;
+            else if (pad == SIGOPS_PAD_MIRROR) {
+                const int64_t cnt = idx / I.i1, rem = idx % I.i1;
+                idx = (cnt & 1) ? (I.i1 - 1 - rem) : rem;
+            } else idx = I.i1 - 1;
+        }
+        out[j] = use_pad ? I.d0 : load_elem(b.ptr, b.dtype, (int64_t)ch * b.ld + idx);
+    }
+}
+
+// Evaluate a program for V samples n[j] = n0 + j*nstride of channel c (nstride must be
+// the stride prepare_program was given).  `stack` is this thread's spill area, laid out
+// [depth][V] with stride `sstride` doubles between consecutive slots (so neighbouring
+// threads interleave and stay bank-conflict free).  Each instruction is decoded once
+// (copied to registers) and its leaf is evaluated for all V frames by a vector routine.
 template <int V>
 __device__ __forceinline__ void eval_program(const sigops_instr* sprog, const double* leafconst,
-                                             int len, const Env& env, int64_t n0, int64_t nstride,
-                                             int c, const double* stageval, double* acc,
-                                             double* stack, int sstride) {
+                                             const double2* leafrot, int len, const Env& env,
+                                             int64_t n0, int64_t nstride, int c, const double* stageval,
+                                             double* acc, double* stack, int sstride) {
     int sp = 0;
 #pragma unroll
     for (int j = 0; j < V; ++j) acc[j] = 0.0;
     for (int pc = 0; pc < len; ++pc) {
-        const sigops_instr& I = sprog[pc];
+        const sigops_instr I = sprog[pc];
         const int op = I.op;
         if (op <= SIGOPS_OP_DIV) {
+            double v[V];
+            switch (I.leaf) {
+                case SIGOPS_LEAF_CONST:
+                case SIGOPS_LEAF_RMS: {
+                    const double k = leafconst[pc];
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                const double v = leaf_value(I, env, leafconst, pc, n0 + j * nstride, c,
-                                            stageval ? stageval[j] : 0.0);
-                acc[j] = (op == SIGOPS_OP_LOAD) ? v : binop(op, acc[j], v);
+                    for (int j = 0; j < V; ++j) v[j] = k;
+                    break;
+                }
+                case SIGOPS_LEAF_BUF:
+                    buf_values<V>(I, env, n0, nstride, c, v);
+                    break;
+                case SIGOPS_LEAF_STAGE:
+#pragma unroll
+                    for (int j = 0; j < V; ++j) v[j] = stageval[j];
+                    break;
+                case SIGOPS_LEAF_GEN:
+                    if (V > 1 && gen_is_trig(I)) {
+                        gen_trig_values<V>(I, leafrot[pc], n0 + I.i0, v);
+                        break;
+                    }
+                    // fall through
+                default:
+#pragma unroll
+                    for (int j = 0; j < V; ++j)
+                        v[j] = leaf_value(I, env, leafconst, pc, n0 + j * nstride, c, stageval ? stageval[j] : 0.0);
+            }
+            switch (op) {
+                case SIGOPS_OP_LOAD:
+#pragma unroll
+                    for (int j = 0; j < V; ++j) acc[j] = v[j];
+                    break;
+                case SIGOPS_OP_ADD:
+#pragma unroll
+                    for (int j = 0; j < V; ++j) acc[j] += v[j];
+                    break;
+                case SIGOPS_OP_SUB:
+#pragma unroll
+                    for (int j = 0; j < V; ++j) acc[j] -= v[j];
+                    break;
+                case SIGOPS_OP_MUL:
+#pragma unroll
+                    for (int j = 0; j < V; ++j) acc[j] *= v[j];
+                    break;
+                default:
+#pragma unroll
+                    for (int j = 0; j < V; ++j) acc[j] /= v[j];
             }
         } else if (op == SIGOPS_OP_PUSH) {
 #pragma unroll

@@ -73,6 +73,7 @@ k_fir(const __grid_constant__ FirParams P) {
     constexpr int kFirYPitch = kFirT + 2;       // doubles; = 2 mod 4 keeps lane=row 128-bit stores conflict free
     __shared__ sigops_instr sprog_epi[SIGOPS_MAX_PROG];
     __shared__ double lc_epi[W][SIGOPS_MAX_PROG];
+    __shared__ double2 lr_epi[SIGOPS_MAX_PROG];
     __shared__ int s_ws[kFirT];                           // window start of output m relative to the tile
     extern __shared__ __align__(16) double smem[];
     double* hm = smem;                                    // [T][tpad]
@@ -171,7 +172,18 @@ k_fir(const __grid_constant__ FirParams P) {
     asm volatile("cp.async.commit_group;" ::: "memory");
 
     // ---- 2. merged taps while the copies fly: 4 threads per output
-    for (int i = tid; i < P.epi_prog_len; i += kFirThreads) sprog_epi[i] = P.instrs[P.epi_prog_start + i];
+    for (int i = tid; i < P.epi_prog_len; i += kFirThreads) {
+        const sigops_instr I = P.instrs[P.epi_prog_start + i];
+        sprog_epi[i] = I;
+        double2 rot = make_double2(0.0, 1.0);
+        if (I.leaf == SIGOPS_LEAF_GEN && gen_is_trig(I)) {       // one-frame phase advance (see prepare_program)
+            const double w = (I.flags & SIGOPS_FLAG_HAS_OMEGA) ? I.d1 : 1.0;
+            double cyc = 1.0 / I.d0 * w;
+            if (!(I.flags & SIGOPS_FLAG_HAS_OMEGA) && I.fn != SIGOPS_FN_SIN) cyc *= 0.15915494309189535;
+            sincospi(2.0 * cyc, &rot.x, &rot.y);
+        }
+        lr_epi[i] = rot;
+    }
     {
         const int m = my_m, sub = tid & 3;
         const int ws = (int)(my_xi0 - P.tapsper + 1 - p0);            // >= 0
@@ -309,7 +321,7 @@ k_fir(const __grid_constant__ FirParams P) {
         __syncwarp();
         const double y[2] = {yv.x, yv.y};
         double o[2];
-        eval_program<2>(sprog_epi, lc_epi[warp], P.epi_prog_len, env, m, 1, c, y, o, stack + tid, kFirThreads);
+        eval_program<2>(sprog_epi, lc_epi[warp], lr_epi, P.epi_prog_len, env, m, 1, c, y, o, stack + tid, kFirThreads);
         __syncwarp();
         double ss = 0.0;
         const BufRef ob = bufs[P.out_buf];

@@ -293,6 +293,7 @@ k_iir(const __grid_constant__ IirParams P) {
     __shared__ sigops_instr sprog_in[SIGOPS_MAX_PROG];
     __shared__ sigops_instr sprog_epi[SIGOPS_MAX_PROG];
     __shared__ double lc_in[SIGOPS_MAX_PROG], lc_epi[SIGOPS_MAX_PROG];
+    __shared__ double2 lr_in[SIGOPS_MAX_PROG], lr_epi[SIGOPS_MAX_PROG];
     __shared__ BufRef sbufs[32];
     __shared__ double tiles[kIirWarps][32 * kTilePitch];
     extern __shared__ double stack[];
@@ -304,8 +305,8 @@ k_iir(const __grid_constant__ IirParams P) {
 
     for (int i = threadIdx.x; i < P.nbuf; i += blockDim.x) sbufs[i] = P.bufrefs[(size_t)inst * P.nbuf + i];
     Env env{sbufs, P.scalars + (size_t)inst * P.nscalars};
-    prepare_program(P.instrs + P.in_prog_start, P.in_prog_len, sprog_in, lc_in, env);
-    prepare_program(P.instrs + P.epi_prog_start, P.epi_prog_len, sprog_epi, lc_epi, env);
+    prepare_program(P.instrs + P.in_prog_start, P.in_prog_len, sprog_in, lc_in, lr_in, env, P.L);
+    prepare_program(P.instrs + P.epi_prog_start, P.epi_prog_len, sprog_epi, lc_epi, lr_epi, env, P.L);
     __syncthreads();
 
     double* tile = tiles[warp];
@@ -347,7 +348,7 @@ k_iir(const __grid_constant__ IirParams P) {
                         v[j] = (n < P.plain_in_len) ? load_elem(ib.ptr, ib.dtype, (int64_t)c * ib.ld + n) : 0.0;
                     }
                 } else {
-                    eval_program<kIirV>(sprog_in, lc_in, P.in_prog_len, env, n0, P.L, c, nullptr, v,
+                    eval_program<kIirV>(sprog_in, lc_in, lr_in, P.in_prog_len, env, n0, P.L, c, nullptr, v,
                                         stack + threadIdx.x, kIirThreads);
                 }
             } else {
@@ -384,7 +385,7 @@ k_iir(const __grid_constant__ IirParams P) {
 #pragma unroll
             for (int j = 0; j < kIirV; ++j) y[j] = tile[(r + j) * kTilePitch + lane];
             if (P.epi_prog_len > 0)
-                eval_program<kIirV>(sprog_epi, lc_epi, P.epi_prog_len, env, n0, P.L, c, y, o,
+                eval_program<kIirV>(sprog_epi, lc_epi, lr_epi, P.epi_prog_len, env, n0, P.L, c, y, o,
                                     stack + threadIdx.x, kIirThreads);
             else {
 #pragma unroll
@@ -438,21 +439,31 @@ struct CarryParams {
 };
 
 __global__ void k_iir_carry(const CarryParams P) {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per row; lane i owns state component i (2M <= 16 lanes busy), so a chunk step is
+    // one coalesced load, 2M shuffles + FMAs and one coalesced store instead of (2M)^2 scalar loads
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= P.nrows) return;
     const int64_t nslots = P.nrows * P.slots_per_row;
-    double s[2 * kIirMaxSections], t[2 * kIirMaxSections];
-    for (int i = 0; i < P.M2; ++i) s[i] = 0.0;
+    const bool on = lane < P.M2;
+    double a_row[2 * kIirMaxSections];
+#pragma unroll
+    for (int j = 0; j < 2 * kIirMaxSections; ++j) a_row[j] = (P.AL && on && j < P.M2) ? P.AL[lane * P.M2 + j] : 0.0;
+    double s = 0.0;
+    // software prefetch: the zero-state results do not depend on the carry
+    double zs_next = (on && P.nchunks > 0) ? P.state_zs[(int64_t)lane * nslots + row * P.slots_per_row] : 0.0;
     for (int64_t k = 0; k < P.nchunks; ++k) {
         const int64_t slot = row * P.slots_per_row + k;
-        for (int i = 0; i < P.M2; ++i) P.state_in[i * nslots + slot] = s[i];
-        for (int i = 0; i < P.M2; ++i) {
-            double a = P.state_zs[i * nslots + slot];
-            if (P.AL)
-                for (int j = 0; j < P.M2; ++j) a = fma(P.AL[i * P.M2 + j], s[j], a);
-            t[i] = a;
+        const double zs = zs_next;
+        if (k + 1 < P.nchunks && on) zs_next = P.state_zs[(int64_t)lane * nslots + slot + 1];
+        if (on) P.state_in[(int64_t)lane * nslots + slot] = s;
+        double t = zs;
+#pragma unroll
+        for (int j = 0; j < 2 * kIirMaxSections; ++j) {
+            const double sj = __shfl_sync(0xffffffffu, s, j);
+            if (j < P.M2) t = fma(a_row[j], sj, t);
         }
-        for (int i = 0; i < P.M2; ++i) s[i] = t[i];
+        s = t;
     }
 }
 

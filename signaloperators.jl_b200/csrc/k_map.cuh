@@ -9,15 +9,16 @@
 // a leaf of the consumer's program.
 //
 // HBM-bound: 8(k+1) bytes per output sample for k buffer leaves.
-// Layout: thread t of a 256-thread block owns frames t, t+256, t+512, t+768 of a
-// 1024-frame tile, so every warp access is a fully coalesced 256-byte row.
+// Layout: thread t of a 256-thread block owns frames t, t+256, ..., t+1792 of a
+// 2048-frame tile, so every warp access is a fully coalesced 256-byte row; the eight
+// frames share one decode of each program instruction.
 #pragma once
 #include "interp.cuh"
 
 namespace sigops {
 
 constexpr int kMapThreads = 256;
-constexpr int kMapV = 4;
+constexpr int kMapV = 8;
 constexpr int kMapTile = kMapThreads * kMapV;
 constexpr int kMaxPieces = 64;
 constexpr int kMaxBufs = 32;
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(kMapThreads)
 k_map(const __grid_constant__ MapParams P) {
     __shared__ sigops_instr sprog[SIGOPS_MAX_PROG];
     __shared__ double leafconst[SIGOPS_MAX_PROG];
+    __shared__ double2 leafrot[SIGOPS_MAX_PROG];
     __shared__ BufRef sbufs[kMaxBufs];
     __shared__ double red[kMapThreads / 32];
     extern __shared__ double stack[];
@@ -49,7 +51,7 @@ k_map(const __grid_constant__ MapParams P) {
 
     for (int i = threadIdx.x; i < P.nbuf; i += blockDim.x) sbufs[i] = P.bufrefs[(size_t)inst * P.nbuf + i];
     Env env{sbufs, P.scalars + (size_t)inst * P.nscalars};
-    prepare_program(P.instrs + pc.prog_start, pc.prog_len, sprog, leafconst, env);
+    prepare_program(P.instrs + pc.prog_start, pc.prog_len, sprog, leafconst, leafrot, env, kMapThreads);
     __syncthreads();
 
     const int64_t tile = (int64_t)blockIdx.x - P.tile_prefix[p];
@@ -57,17 +59,27 @@ k_map(const __grid_constant__ MapParams P) {
     const int64_t nend = pc.out_start + pc.out_len;
 
     double acc[kMapV];
-    eval_program<kMapV>(sprog, leafconst, pc.prog_len, env, n0, kMapThreads, c, nullptr, acc,
+    eval_program<kMapV>(sprog, leafconst, leafrot, pc.prog_len, env, n0, kMapThreads, c, nullptr, acc,
                         stack + threadIdx.x, kMapThreads);
 
     const BufRef ob = sbufs[P.out_buf];
     double ss = 0.0;
+    if (ob.dtype == SIGOPS_F64) {
+        double* op = reinterpret_cast<double*>(ob.ptr) + (int64_t)c * ob.ld + n0;
 #pragma unroll
-    for (int j = 0; j < kMapV; ++j) {
-        const int64_t n = n0 + (int64_t)j * kMapThreads;
-        if (n < nend) {
-            const double v = store_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + n, acc[j]);
-            ss += v * v;
+        for (int j = 0; j < kMapV; ++j)
+            if (n0 + (int64_t)j * kMapThreads < nend) {
+                op[j * kMapThreads] = acc[j];
+                ss = fma(acc[j], acc[j], ss);
+            }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kMapV; ++j) {
+            const int64_t n = n0 + (int64_t)j * kMapThreads;
+            if (n < nend) {
+                const double v = store_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + n, acc[j]);
+                ss += v * v;
+            }
         }
     }
     if (P.sumsq_slot >= 0) {

@@ -613,6 +613,9 @@ IirLaunch choose_iir_chunking_flat(const StageRT& s, int64_t rows, int sm_count)
         const int64_t waves = (blocks + sm_count - 1) / sm_count;
         const double fix = cpr > 1 ? (double)std::min(W64, L) * (W64 >= L ? 1.0 : 1.2) : 0.0;
         double cost = (double)waves * ((double)L + fix + 600.0);      // + fixed per-wave cost (launch, pipeline fill)
+        // slow decay (W >= L): MAIN + CARRY + FIX; the carry walks the chunks of a row one after the
+        // other (one dependent 2Mx2M mat-vec per chunk, ~150 frame-times each)
+        if (cpr > 1 && W64 >= L) cost += (double)L * waves + 150.0 * (double)cpr + 1200.0;
         if (N % L) cost *= 1.02;                                     // ragged last chunk takes the scalar path
         if (cost < best) { best = cost; bestL = L; }
     }
@@ -638,6 +641,9 @@ IirLaunch choose_iir_chunking(const StageRT& s, int64_t rows, int sm_count) {
     IirLaunch r;
     r.blocks_per_row = bpr;
     r.L = Lof(bpr);
+    // a chunk shorter than the decay length would force the MAIN+CARRY+FIX path over every frame:
+    // prefer fewer, longer chunks (idle lanes) as long as a row still splits into >= 8 of them
+    if (r.L <= W32 && 2 * W32 <= N / 8) r.L = round_up(2 * W32, 32);
     r.nchunks = (N + r.L - 1) / r.L;
     r.Wc = std::min(W32, r.L);
     r.need_matrix = s.iir.W >= r.L;
@@ -900,7 +906,7 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                     CUDA_OK(cudaMemcpyAsync(dAL, AL.data(), AL.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
                     CUDA_OK(cudaStreamSynchronize(stream));   // AL is a host temporary
                     C.AL = dAL;
-                    const unsigned cblocks = (unsigned)((rows + 127) / 128);
+                    const unsigned cblocks = (unsigned)((rows + 3) / 4);        // one warp per row
                     add(KIND_IIR_CARRY, [=](cudaStream_t st) { k_iir_carry<<<cblocks, 128, 0, st>>>(C); });
                 }
                 {

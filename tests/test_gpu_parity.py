@@ -50,15 +50,15 @@ def rng(seed=1983):
 # ---- K1: generators, cuts, pads, appends, maps, ramps -------------------------------------
 
 def test_tone(gpu):
-    check(gpu, lambda: Signal(sin, 44.1 * kHz, ω=100 * Hz) >> Until(5 * s), tol=1e-12)
+    check(gpu, lambda: Signal(sin, 44.1 * kHz, ω=100 * Hz) >> Until(5 * s), tol=1e-10)
 
 
 def test_tone_phase_and_no_omega(gpu):
-    check(gpu, lambda: Signal(sin, ω=5 * Hz, ϕ=np.pi) >> Until(1 * s) >> ToFramerate(20 * Hz), tol=1e-12)
-    check(gpu, lambda: Signal(sin, ϕ=1 * s) >> Until(1 * s) >> ToFramerate(20 * Hz), tol=1e-12)
-    check(gpu, lambda: Signal(cos, 100 * Hz, ω=7 * Hz) >> Until(3 * s), tol=1e-12)
-    check(gpu, lambda: Signal(Sawtooth(), 8 * kHz, ω=1 * kHz) >> Until(2 * s), tol=1e-12)
-    check(gpu, lambda: Signal(AffineSin(0.5, 0.5), 8 * kHz, ω=5 * Hz) >> Until(2 * s), tol=1e-12)
+    check(gpu, lambda: Signal(sin, ω=5 * Hz, ϕ=np.pi) >> Until(1 * s) >> ToFramerate(20 * Hz), tol=1e-10)
+    check(gpu, lambda: Signal(sin, ϕ=1 * s) >> Until(1 * s) >> ToFramerate(20 * Hz), tol=1e-10)
+    check(gpu, lambda: Signal(cos, 100 * Hz, ω=7 * Hz) >> Until(3 * s), tol=1e-10)
+    check(gpu, lambda: Signal(Sawtooth(), 8 * kHz, ω=1 * kHz) >> Until(2 * s), tol=1e-10)
+    check(gpu, lambda: Signal(AffineSin(0.5, 0.5), 8 * kHz, ω=5 * Hz) >> Until(2 * s), tol=1e-10)
 
 
 def test_arbitrary_callable_is_host_materialised(gpu):
@@ -82,7 +82,7 @@ def test_cutting(gpu, nch):
     got = check(gpu, lambda: Window(x20, from_=15 * frames, to=25 * frames), exact=True)
     assert np.array_equal(got, x20[15:20])
     check(gpu, lambda: Signal(sin, 200 * Hz, ω=10 * Hz) >> ToChannels(nch) >> Until(10 * frames)
-          >> After(5 * frames) >> After(2 * frames), tol=1e-12)
+          >> After(5 * frames) >> After(2 * frames), tol=1e-10)
     check(gpu, lambda: Signal(sin, 200 * Hz, ω=10 * Hz) >> ToChannels(nch) >> Until(10 * frames)
           >> Until(0 * frames), exact=True)
 
@@ -98,17 +98,17 @@ def test_padding(gpu, nch):
     check(gpu, lambda: Pad(Signal(x, 10 * Hz), lastframe) >> Until(15 * frames), exact=True)
     padv = rng(3).random(nch)
     check(gpu, lambda: Pad(Signal(sin, 10 * Hz) >> ToChannels(nch) >> Until(1 * s), padv)
-          >> Until(15 * frames), tol=1e-12)
+          >> Until(15 * frames), tol=1e-10)
     check(gpu, lambda: Pad(Signal(sin, 10 * Hz) >> ToChannels(nch) >> Until(1 * s), lastframe)
-          >> Until(15 * frames), tol=1e-12)
+          >> Until(15 * frames), tol=1e-10)
     check(gpu, lambda: Signal(sin, 22 * Hz, ω=10 * Hz) >> ToChannels(nch) >> Until(5 * s) >> Pad(one)
-          >> Until(7 * s), tol=1e-12)
+          >> Until(7 * s), tol=1e-10)
 
 
 @pytest.mark.parametrize("nch", [1, 2])
 def test_appending_and_padded_maps(gpu, nch):
     check(gpu, lambda: (Signal(sin, 22 * Hz, ω=10 * Hz) >> ToChannels(nch) >> Until(5 * s))
-          >> Append(Signal(sin, 22 * Hz, ω=5 * Hz) >> ToChannels(nch) >> Until(5 * s)), tol=1e-12)
+          >> Append(Signal(sin, 22 * Hz, ω=5 * Hz) >> ToChannels(nch) >> Until(5 * s)), tol=1e-10)
 
     def ab():
         a = Signal(2, 3 * Hz) >> ToChannels(nch) >> Until(2 * s) >> Append(Signal(3, 3 * Hz)) >> Until(4 * s)
@@ -142,19 +142,19 @@ def test_channel_ops(gpu):
 
 @pytest.mark.parametrize("nch", [1, 2])
 def test_ramps(gpu, nch):
-    check(gpu, lambda: Signal(sin, 50 * Hz, ω=10 * Hz) >> ToChannels(nch) >> Until(5 * s) >> Ramp(500 * ms), tol=1e-12)
+    check(gpu, lambda: Signal(sin, 50 * Hz, ω=10 * Hz) >> ToChannels(nch) >> Until(5 * s) >> Ramp(500 * ms), tol=1e-10)
     check(gpu, lambda: Signal(sin, 500 * Hz, ω=20 * Hz, ϕ=np.pi / 2) >> ToChannels(nch) >> Until(100 * ms)
-          >> Ramp(identity), tol=1e-12)
+          >> Ramp(identity), tol=1e-10)
     check(gpu, lambda: Signal(sin, 500 * Hz, ω=20 * Hz) >> ToChannels(nch) >> Until(100 * ms)
-          >> RampOn(20 * ms, lambda v: v * v), tol=1e-12)
+          >> RampOn(20 * ms, lambda v: v * v), tol=1e-10)
     check(gpu, lambda: Signal(sin, 500 * Hz, ω=20 * Hz) >> ToChannels(nch) >> Until(100 * ms)
-          >> RampOff(20 * ms, lambda v: v ** 3), tol=1e-12)
+          >> RampOff(20 * ms, lambda v: v ** 3), tol=1e-10)
 
     def fade():
         a = Signal(sin, 22 * Hz, ω=10 * Hz) >> ToChannels(nch) >> Until(2 * s)
         b = Signal(sin, 22 * Hz, ω=5 * Hz) >> ToChannels(nch) >> Until(2 * s)
         return FadeTo(a, b, 500 * ms)
-    got = check(gpu, fade, tol=1e-12)
+    got = check(gpu, fade, tol=1e-10)
     assert got.shape[0] == int(np.ceil((2 + 2 - 0.5) * 22))
 
 
@@ -163,13 +163,13 @@ def test_ramps(gpu, nch):
 @pytest.mark.parametrize("nch", [1, 2])
 def test_normpower(gpu, nch):
     got = check(gpu, lambda: Signal(sin, 10 * Hz, ω=2 * Hz) >> ToChannels(nch) >> Until(2 * s) >> Ramp() >> Normpower,
-                tol=1e-12)
+                tol=1e-10)
     assert abs(rms(got) - 1) < 1e-12
     x = rng().standard_normal((5000, nch))
-    got = check(gpu, lambda: Signal(x, 1 * kHz) >> Normpower >> Amplify(-10 * dB), tol=1e-12)
+    got = check(gpu, lambda: Signal(x, 1 * kHz) >> Normpower >> Amplify(-10 * dB), tol=1e-10)
     check(gpu, lambda: Mix(Signal(x, 1 * kHz) >> Normpower, Signal(sin, 1 * kHz, ω=50 * Hz) >> Until(2 * s)
-                           >> Normpower >> Amplify(-6 * dB)), tol=1e-12)
-    check(gpu, lambda: Signal(x, 1 * kHz) >> Normpower >> After(1 * s) >> Until(2 * s), tol=1e-12)
+                           >> Normpower >> Amplify(-6 * dB)), tol=1e-10)
+    check(gpu, lambda: Signal(x, 1 * kHz) >> Normpower >> After(1 * s) >> Until(2 * s), tol=1e-10)
 
 
 # ---- K3: IIR ------------------------------------------------------------------------------------
