@@ -34,7 +34,7 @@ struct MapParams {
     int tile_prefix[kMaxPieces + 1];
 };
 
-__global__ void __launch_bounds__(kMapThreads)
+__global__ void __launch_bounds__(kMapThreads, 4)
 k_map(const __grid_constant__ MapParams P) {
     __shared__ sigops_instr sprog[SIGOPS_MAX_PROG];
     __shared__ double leafconst[SIGOPS_MAX_PROG];

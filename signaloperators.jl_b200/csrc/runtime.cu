@@ -99,6 +99,12 @@ struct Arena {
         used = off + bytes;
         return base + off;
     }
+    void* take_packed(size_t bytes) {      // 16-byte granularity: consecutive takes stay adjacent
+        size_t off = (used + 15) & ~size_t(15);
+        if (off + bytes > cap) fail(SIGOPS_ERR_NOMEM, "internal: arena overflow (%zu > %zu)", off + bytes, cap);
+        used = off + bytes;
+        return base + off;
+    }
     void release() {
         if (base) cudaFree(base);
         base = nullptr;
@@ -1023,6 +1029,41 @@ int64_t run_device_resident(sigops_plan& p, int di, int64_t ninst, const sigops_
     return launches;
 }
 
+// Copy buffer `b` of `w` consecutive instances between host and device staging.  A buffer whose
+// rows are dense (ld == nframes on both sides) is one contiguous block; blocks of consecutive
+// instances that are adjacent on both sides are merged, so a batch held in one big host array
+// moves with a single cudaMemcpyAsync per buffer slot instead of one 2-D copy per instance.
+int64_t copy_runs(const sigops_buffer* host, const sigops_buffer* dev, int64_t w, uint32_t nb, bool to_device, cudaStream_t st) {
+    int64_t total = 0;
+    for (uint32_t b = 0; b < nb; ++b) {
+        int64_t i = 0;
+        while (i < w) {
+            const sigops_buffer& hb = host[i * nb + b];
+            const sigops_buffer& db = dev[i * nb + b];
+            const size_t es = elem_size(hb.dtype);
+            if (hb.nframes == 0) { ++i; continue; }
+            const bool dense = hb.ld == hb.nframes && db.ld == hb.nframes;
+            if (!dense) {
+                if (to_device) CUDA_OK(cudaMemcpy2DAsync(db.ptr, db.ld * es, hb.ptr, hb.ld * es, hb.nframes * es, hb.nchannels, cudaMemcpyHostToDevice, st));
+                else CUDA_OK(cudaMemcpy2DAsync(hb.ptr, hb.ld * es, db.ptr, db.ld * es, hb.nframes * es, hb.nchannels, cudaMemcpyDeviceToHost, st));
+                total += hb.nframes * hb.nchannels * (int64_t)es;
+                ++i;
+                continue;
+            }
+            const size_t bytes = (size_t)hb.nframes * hb.nchannels * es;
+            int64_t j = i + 1;
+            while (j < w && (char*)host[j * nb + b].ptr == (char*)hb.ptr + (j - i) * bytes &&
+                   (char*)dev[j * nb + b].ptr == (char*)db.ptr + (j - i) * bytes)
+                ++j;
+            if (to_device) CUDA_OK(cudaMemcpyAsync(db.ptr, hb.ptr, bytes * (j - i), cudaMemcpyHostToDevice, st));
+            else CUDA_OK(cudaMemcpyAsync(hb.ptr, db.ptr, bytes * (j - i), cudaMemcpyDeviceToHost, st));
+            total += (int64_t)bytes * (j - i);
+            i = j;
+        }
+    }
+    return total;
+}
+
 // ---- host-buffer run: H2D -> stages -> D2H, two pipeline slots per device ----------
 
 struct HostRunResult {
@@ -1078,41 +1119,30 @@ void run_host_on_device(sigops_plan& p, int di, int64_t i_begin, int64_t i_end, 
             din.assign((size_t)w * nin, sigops_buffer{});
             dout.assign((size_t)w * nout, sigops_buffer{});
             CUDA_OK(cudaEventRecord(slot.ev[0], st));
-            for (int64_t i = 0; i < w; ++i) {
-                for (uint32_t b = 0; b < nin; ++b) {
+            // device staging: buffer-major so that the same buffer of consecutive instances is
+            // contiguous; host runs that are contiguous too (one big batch array) become ONE copy
+            for (uint32_t b = 0; b < nin; ++b)
+                for (int64_t i = 0; i < w; ++i) {
                     const sigops_buffer& hb = in[(i_begin + i0 + i) * nin + b];
                     sigops_buffer& db = din[i * nin + b];
                     db = hb;
                     db.ld = round_up(std::max<int64_t>(hb.nframes, 1), 16);
-                    const size_t es = elem_size(hb.dtype);
-                    db.ptr = slot.arena.take((size_t)db.ld * hb.nchannels * es);
-                    if (hb.nframes > 0) {
-                        CUDA_OK(cudaMemcpy2DAsync(db.ptr, db.ld * es, hb.ptr, hb.ld * es, hb.nframes * es, hb.nchannels, cudaMemcpyHostToDevice, st));
-                        res.h2d += hb.nframes * hb.nchannels * (int64_t)es;
-                    }
+                    db.ptr = slot.arena.take_packed((size_t)db.ld * hb.nchannels * elem_size(hb.dtype));
                 }
-                for (uint32_t b = 0; b < nout; ++b) {
+            for (uint32_t b = 0; b < nout; ++b)
+                for (int64_t i = 0; i < w; ++i) {
                     const sigops_buffer& hb = out[(i_begin + i0 + i) * nout + b];
                     sigops_buffer& db = dout[i * nout + b];
                     db = hb;
                     db.ld = round_up(std::max<int64_t>(hb.nframes, 1), 16);
-                    db.ptr = slot.arena.take((size_t)db.ld * hb.nchannels * elem_size(hb.dtype));
+                    db.ptr = slot.arena.take_packed((size_t)db.ld * hb.nchannels * elem_size(hb.dtype));
                 }
-            }
+            res.h2d += copy_runs(in + (i_begin + i0) * nin, din.data(), w, nin, true, st);
             CUDA_OK(cudaEventRecord(slot.ev[1], st));
             WaveIO io{w, din.data(), dout.data()};
             res.launches += enqueue_wave(p, di, slot, st, io);
             CUDA_OK(cudaEventRecord(slot.ev[2], st));
-            for (int64_t i = 0; i < w; ++i)
-                for (uint32_t b = 0; b < nout; ++b) {
-                    const sigops_buffer& hb = out[(i_begin + i0 + i) * nout + b];
-                    const sigops_buffer& db = dout[i * nout + b];
-                    const size_t es = elem_size(hb.dtype);
-                    if (hb.nframes > 0) {
-                        CUDA_OK(cudaMemcpy2DAsync(hb.ptr, hb.ld * es, db.ptr, db.ld * es, hb.nframes * es, hb.nchannels, cudaMemcpyDeviceToHost, st));
-                        res.d2h += hb.nframes * hb.nchannels * (int64_t)es;
-                    }
-                }
+            res.d2h += copy_runs(out + (i_begin + i0) * nout, dout.data(), w, nout, false, st);
             CUDA_OK(cudaEventRecord(slot.ev[3], st));
         }
         for (int s = 0; s < std::min(k, 2); ++s) {
