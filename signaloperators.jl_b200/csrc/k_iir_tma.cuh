@@ -62,15 +62,32 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// 16 frames (one quarter of a stage) through the cascade; see cascade_tile in k_iir.cuh.
-// Returns sum(out^2) of the 16 outputs.
-template <int M, bool ZERO_IN, bool UNITB>
-__device__ __forceinline__ double cascade16(Cascade<M>& f, double* p, double gain, double sc) {
+// Fused elementwise programs of the TMA kernel (PROG variants): the input program sees the
+// frame just loaded as LEAF_STAGE (e.g. `load * modulator`), the epilogue sees the filter
+// output as LEAF_STAGE (e.g. `y * ramp_on * ramp_off + tone`).  Neither may read another
+// buffer or an RMS slot (the planner falls back to k_iir for those).
+struct TmaProg {
+    const sigops_instr* in_prog;  const double* in_lc;  const double2* in_rot;  int in_len;
+    const sigops_instr* ep_prog;  const double* ep_lc;  const double2* ep_rot;  int ep_len;
+};
+
+// 16 frames (one third of a stage) through the cascade; see cascade_tile in k_iir.cuh.
+// Returns sum(out^2) of the 16 outputs.  n0 = signal frame of p[0], c = channel (PROG only).
+template <int M, bool ZERO_IN, bool UNITB, bool PROG>
+__device__ __forceinline__ double cascade16(Cascade<M>& f, double* p, double gain, double sc,
+                                            const TmaProg& T, int64_t n0, int c) {
     double xr[16];
 #pragma unroll
     for (int k = 0; k < 16; k += 2) {
         const double2 v = *reinterpret_cast<const double2*>(p + k);
         xr[k] = v.x; xr[k + 1] = v.y;
+    }
+    if (PROG && T.in_len > 0) {
+        double t[16];
+        Env env{nullptr, nullptr};
+        eval_program<16>(T.in_prog, T.in_lc, T.in_rot, T.in_len, env, n0, 1, c, xr, t, nullptr, 0);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) xr[k] = t[k];
     }
     double pipe[M], out[16];
 #pragma unroll
@@ -84,6 +101,13 @@ __device__ __forceinline__ double cascade16(Cascade<M>& f, double* p, double gai
                 if (j == M - 1) out[k] = ZERO_IN ? fma(pipe[j], gain, xr[k]) * sc : (pipe[j] * gain) * sc;
             }
         }
+    }
+    if (PROG && T.ep_len > 0) {
+        double t[16];
+        Env env{nullptr, nullptr};
+        eval_program<16>(T.ep_prog, T.ep_lc, T.ep_rot, T.ep_len, env, n0, 1, c, out, t, nullptr, 0);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) out[k] = t[k];
     }
     double ss = 0.0;
 #pragma unroll
@@ -101,11 +125,21 @@ struct IirTmaParams {
     int64_t total_chunks;   // rows * cpr
 };
 
-template <int M, int MODE, bool UNITB>
+template <int M, int MODE, bool UNITB, bool PROG>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 k_iir_tma(const __grid_constant__ IirTmaParams Q) {
     const IirParams& P = Q.base;
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ sigops_instr sp_in[PROG ? SIGOPS_MAX_PROG : 1], sp_ep[PROG ? SIGOPS_MAX_PROG : 1];
+    __shared__ double lc_in[PROG ? SIGOPS_MAX_PROG : 1], lc_ep[PROG ? SIGOPS_MAX_PROG : 1];
+    __shared__ double2 lr_in[PROG ? SIGOPS_MAX_PROG : 1], lr_ep[PROG ? SIGOPS_MAX_PROG : 1];
+    TmaProg T{sp_in, lc_in, lr_in, PROG ? P.in_prog_len : 0, sp_ep, lc_ep, lr_ep, PROG ? P.epi_prog_len : 0};
+    if (PROG) {
+        Env env0{nullptr, nullptr};
+        prepare_program(P.instrs + P.in_prog_start, P.in_prog_len, sp_in, lc_in, lr_in, env0, 1);
+        prepare_program(P.instrs + P.epi_prog_start, P.epi_prog_len, sp_ep, lc_ep, lr_ep, env0, 1);
+        __syncthreads();
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // per warp: [stage 0/1][lane][kStagePitch] doubles (lane stride 132 words = 4 mod 32 banks:
     // 128-bit lane=row accesses are conflict free), then two mbarriers per lane
@@ -196,15 +230,25 @@ k_iir_tma(const __grid_constant__ IirTmaParams Q) {
         }
         const int64_t off = h * kStageCols;
         const double sc = (off < raw_frames) ? 1.0 : sc_final;      // Wc is a multiple of the stage
-        double s4 = cascade16<M, MODE == IIR_FIX, UNITB>(f, buf, P.gain, sc);
+        const int64_t nstage0 = k * L - pre + off;                 // signal frame of buf[0]
+        double s4;
+        if (PROG) s4 = 0.0;
+        else s4 = cascade16<M, MODE == IIR_FIX, UNITB, PROG>(f, buf, P.gain, sc, T, nstage0, c);
         // the other stage was handed to a bulk store one iteration ago: once the TMA has
         // read it, start filling it with the next stage
         if (h + 1 < nstage) {
             bulk_wait_read_all();
             issue_load(h + 1);
         }
+        if (PROG) {          // the interpreter is big: keep one copy of it (all three blocks in one loop)
+#pragma unroll 1
+            for (int q = 0; q < kStageCols; q += 16)
+                s4 += cascade16<M, MODE == IIR_FIX, UNITB, PROG>(f, buf + q, P.gain, sc, T, nstage0 + q, c);
+        } else {
 #pragma unroll
-        for (int q = 16; q < kStageCols; q += 16) s4 += cascade16<M, MODE == IIR_FIX, UNITB>(f, buf + q, P.gain, sc);
+            for (int q = 16; q < kStageCols; q += 16)
+                s4 += cascade16<M, MODE == IIR_FIX, UNITB, PROG>(f, buf + q, P.gain, sc, T, nstage0 + q, c);
+        }
         const int64_t rem = work - off;
         if (off < skip_frames) {
             // warm-up stage: outputs are not part of this chunk (pre is a multiple of the stage)

@@ -22,9 +22,10 @@
 #include <cuda_runtime.h>
 
 #include "../../include/signalops.h"
+#include "common.h"
+#include "launchers.h"
+#include "k_iir_carry.cuh"
 #include "k_fir.cuh"
-#include "k_iir.cuh"
-#include "k_iir_tma.cuh"
 #include "k_map.cuh"
 
 static_assert(sizeof(sigops_instr) == 80, "ABI: sigops_instr");
@@ -38,44 +39,6 @@ using namespace sigops;
 namespace {
 
 thread_local std::string g_tls_error = "";
-
-struct Failure {
-    int code;
-    std::string msg;
-};
-
-[[noreturn]] void fail(int code, const char* fmt, ...) {
-    char buf[1024];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    throw Failure{code, buf};
-}
-
-#define CUDA_OK(expr)                                                                       \
-    do {                                                                                    \
-        cudaError_t e__ = (expr);                                                           \
-        if (e__ != cudaSuccess)                                                             \
-            fail(e__ == cudaErrorMemoryAllocation ? SIGOPS_ERR_NOMEM : SIGOPS_ERR_CUDA,    \
-                 "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__,   \
-                 cudaGetErrorString(e__));                                                  \
-    } while (0)
-
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device, size)
-std::mutex g_attr_mu;
-std::unordered_map<const void*, std::pair<uint64_t, size_t>> g_attr_done;
-template <class K>
-void ensure_dyn_smem(K kernel, size_t bytes) {
-    int devno = 0;
-    cudaGetDevice(&devno);
-    std::lock_guard<std::mutex> lk(g_attr_mu);
-    auto& e = g_attr_done[(const void*)kernel];
-    if ((e.first >> (devno & 63) & 1) && e.second >= bytes) return;
-    CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    e.first |= uint64_t(1) << (devno & 63);
-    e.second = std::max(e.second, bytes);
-}
 
 size_t elem_size(int dtype) { return dtype == SIGOPS_F32 ? 4 : 8; }
 int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
@@ -175,6 +138,8 @@ struct IirDerived {
     int plain_buf = -1;
     int64_t plain_len = 0;
     bool fast = false;             // k_iir_fast applies (f64 in/out, constant-gain epilogue)
+    bool tma_prog = false;         // k_iir_tma<PROG>: one plain f64 buffer + buffer-free programs
+    int prog_in_start = 0, prog_in_len = 0;   // input program with the buffer leaf turned into LEAF_STAGE
     bool unitb = false;            // every section has b0 == 1 and b2 == 1 exactly
     int n_scale = 0;
     double scale[2] = {1.0, 1.0};
@@ -373,6 +338,42 @@ void derive_iir(sigops_plan& p, StageRT& s, int idx) {
     }
     s.iir.fast = epi_ok && s.iir.plain_in && p.bufs[s.iir.plain_buf].dtype == SIGOPS_F64 &&
                  p.bufs[st.out_buf].dtype == SIGOPS_F64;
+    // TMA + fused programs: the input program reads exactly one plain Float64 buffer, nothing else
+    // in either program touches a buffer or an RMS slot
+    if (!s.iir.fast && p.bufs[st.out_buf].dtype == SIGOPS_F64) {
+        int nbuf_leaves = 0, bufpc = -1;
+        bool ok = true;
+        auto scan = [&](int start, int len, bool is_input) {
+            for (int i = 0; i < len; ++i) {
+                const sigops_instr& I = p.instrs[start + i];
+                if (I.op > SIGOPS_OP_DIV) { if (I.op == SIGOPS_OP_PUSH) ok = false; continue; }   // no stack in this path
+                if (I.leaf == SIGOPS_LEAF_RMS || I.leaf == SIGOPS_LEAF_CHANSUM) ok = false;
+                if (I.leaf == SIGOPS_LEAF_BUF) {
+                    if (!is_input) { ok = false; continue; }
+                    ++nbuf_leaves;
+                    bufpc = start + i;
+                    if (!(I.i0 == 0 && I.c_mul == 1 && I.c_off == 0 && ((I.flags >> 1) & 3) == SIGOPS_PAD_CONST && I.d0 == 0.0 &&
+                          p.bufs[I.buf].dtype == SIGOPS_F64))
+                        ok = false;
+                }
+            }
+        };
+        scan(st.in_prog_start, st.in_prog_len, true);
+        scan(st.epi_prog_start, st.epi_prog_len, false);
+        if (ok && nbuf_leaves == 1) {
+            s.iir.tma_prog = true;
+            s.iir.plain_buf = p.instrs[bufpc].buf;
+            s.iir.plain_len = p.instrs[bufpc].i1;
+            s.iir.prog_in_start = (int)p.instrs.size();
+            s.iir.prog_in_len = st.in_prog_len;
+            for (int i = 0; i < st.in_prog_len; ++i) {
+                sigops_instr I = p.instrs[st.in_prog_start + i];
+                if (st.in_prog_start + i == bufpc) { I.leaf = SIGOPS_LEAF_STAGE; I.buf = 0; }
+                p.instrs.push_back(I);
+            }
+            if (s.iir.prog_in_len == 1) s.iir.prog_in_len = 0;      // bare load: nothing to evaluate
+        }
+    }
 }
 
 constexpr size_t kFirSmemLimit = 200 * 1024;
@@ -680,7 +681,7 @@ size_t iir_state_bytes(const sigops_plan& p, int64_t ninst, int sm_count) {
         const int64_t rows = ninst * s.st.nchannels;
         const IirLaunch a = choose_iir_chunking(s, rows, sm_count);
         size_t slots = (size_t)rows * a.blocks_per_row * kIirThreads;
-        if (s.iir.fast) slots = std::max(slots, (size_t)rows * choose_iir_chunking_flat(s, rows, sm_count).nchunks);
+        if (s.iir.fast || s.iir.tma_prog) slots = std::max(slots, (size_t)rows * choose_iir_chunking_flat(s, rows, sm_count).nchunks);
         total += (size_t)2 * (2 * s.iir.M) * slots * sizeof(double) + 4096 + 1024;
     }
     return total;
@@ -690,61 +691,6 @@ size_t wave_workspace_bytes(const sigops_plan& p, int64_t ninst, int sm_count) {
     return temp_bytes_per_instance(p) * ninst + iir_state_bytes(p, ninst, sm_count) +
            (size_t)ninst * p.nbuf() * sizeof(BufRef) + (size_t)ninst * std::max<uint32_t>(p.h.n_scalars, 1) * sizeof(double) +
            (1 << 16);
-}
-
-template <int MODE>
-void launch_iir_fast(int M, bool unitb, dim3 grid, cudaStream_t st, const IirParams& P) {
-#define SIGOPS_IIR_CASE(m)                                                  \
-    case m:                                                                 \
-        if (unitb) k_iir_fast<m, MODE, true><<<grid, kIirThreads, 0, st>>>(P);  \
-        else k_iir_fast<m, MODE, false><<<grid, kIirThreads, 0, st>>>(P);       \
-        break;
-    switch (M) {
-        SIGOPS_IIR_CASE(1) SIGOPS_IIR_CASE(2) SIGOPS_IIR_CASE(3) SIGOPS_IIR_CASE(4)
-        SIGOPS_IIR_CASE(5) SIGOPS_IIR_CASE(6) SIGOPS_IIR_CASE(7) SIGOPS_IIR_CASE(8)
-        default: fail(SIGOPS_ERR_UNSUPPORTED, "IIR cascade of %d sections", M);
-    }
-#undef SIGOPS_IIR_CASE
-    CUDA_OK(cudaGetLastError());
-}
-
-constexpr size_t kTmaSmemBytes = (size_t)kTmaThreads * 2 * kStagePitch * sizeof(double) + (size_t)kTmaThreads * 2 * sizeof(uint64_t);
-
-template <int MODE>
-void launch_iir_tma(int M, bool unitb, dim3 grid, cudaStream_t st, const IirTmaParams& Q) {
-#define SIGOPS_IIR_CASE(m)                                                                                          \
-    case m:                                                                                                         \
-        if (unitb) {                                                                                                \
-            ensure_dyn_smem(k_iir_tma<m, MODE, true>, kTmaSmemBytes); \
-            k_iir_tma<m, MODE, true><<<grid, kTmaThreads, kTmaSmemBytes, st>>>(Q);                                   \
-        } else {                                                                                                    \
-            ensure_dyn_smem(k_iir_tma<m, MODE, false>, kTmaSmemBytes); \
-            k_iir_tma<m, MODE, false><<<grid, kTmaThreads, kTmaSmemBytes, st>>>(Q);                                  \
-        }                                                                                                           \
-        break;
-    switch (M) {
-        SIGOPS_IIR_CASE(1) SIGOPS_IIR_CASE(2) SIGOPS_IIR_CASE(3) SIGOPS_IIR_CASE(4)
-        SIGOPS_IIR_CASE(5) SIGOPS_IIR_CASE(6) SIGOPS_IIR_CASE(7) SIGOPS_IIR_CASE(8)
-        default: fail(SIGOPS_ERR_UNSUPPORTED, "IIR cascade of %d sections", M);
-    }
-#undef SIGOPS_IIR_CASE
-    CUDA_OK(cudaGetLastError());
-}
-
-template <int MODE>
-void launch_iir(int M, dim3 grid, size_t smem, cudaStream_t st, const IirParams& P) {
-#define SIGOPS_IIR_CASE(m)                                                                                 \
-    case m:                                                                                                \
-        if (smem > 0) ensure_dyn_smem(k_iir<m, MODE>, smem); \
-        k_iir<m, MODE><<<grid, kIirThreads, smem, st>>>(P);                                                \
-        break;
-    switch (M) {
-        SIGOPS_IIR_CASE(1) SIGOPS_IIR_CASE(2) SIGOPS_IIR_CASE(3) SIGOPS_IIR_CASE(4)
-        SIGOPS_IIR_CASE(5) SIGOPS_IIR_CASE(6) SIGOPS_IIR_CASE(7) SIGOPS_IIR_CASE(8)
-        default: fail(SIGOPS_ERR_UNSUPPORTED, "IIR cascade of %d sections", M);
-    }
-#undef SIGOPS_IIR_CASE
-    CUDA_OK(cudaGetLastError());
 }
 
 // Enqueue every stage of the plan for one wave. Returns kernels launched.
@@ -849,7 +795,7 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
             if (g.n_out == 0) continue;
             const int64_t rows = ninst * g.nchannels;
             // TMA path: fast-path stage whose every channel starts on a 16-byte boundary
-            bool tma = s.iir.fast && !getenv("SIGOPS_NO_TMA");
+            bool tma = (s.iir.fast || s.iir.tma_prog) && !getenv("SIGOPS_NO_TMA");
             if (tma) {
                 for (int64_t i = 0; i < ninst && tma; ++i)
                     for (int b : {s.iir.plain_buf, g.out_buf}) {
@@ -857,14 +803,20 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                         if (((uintptr_t)rb.ptr & 15) || (rb.nch > 1 && (rb.ld & 1))) tma = false;
                     }
             }
-            const IirLaunch c = tma ? choose_iir_chunking_flat(s, rows, dev.sm_count) : choose_iir_chunking(s, rows, dev.sm_count);
+            IirLaunch c = tma ? choose_iir_chunking_flat(s, rows, dev.sm_count) : choose_iir_chunking(s, rows, dev.sm_count);
+            // the program-carrying TMA kernel only exists in the single-launch WARM form
+            const bool tprog = tma && s.iir.tma_prog;
+            if (tprog && c.need_matrix) {
+                tma = false;
+                c = choose_iir_chunking(s, rows, dev.sm_count);
+            }
             IirParams P{};
             P.instrs = pd.instrs; P.bufrefs = d_refs; P.scalars = scalars;
             P.nbuf = nbuf; P.nscalars = nscal;
             P.out_buf = g.out_buf; P.sumsq_slot = g.sumsq_slot;
             P.in_prog_start = g.in_prog_start; P.in_prog_len = g.in_prog_len;
             P.epi_prog_start = g.epi_prog_start; P.epi_prog_len = g.epi_prog_len;
-            P.plain_in_buf = s.iir.plain_in ? s.iir.plain_buf : -1;
+            P.plain_in_buf = (s.iir.plain_in || (tma && s.iir.tma_prog)) ? s.iir.plain_buf : -1;
             P.plain_in_len = s.iir.plain_len;
             P.nch = g.nchannels; P.blocks_per_row = c.blocks_per_row;
             P.N = g.n_out; P.L = c.L; P.Wc = c.Wc;
@@ -882,6 +834,10 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
             P.carry_is_shift = c.need_matrix ? 0 : 1;
             IirTmaParams Q{};
             Q.base = P; Q.cpr = c.nchunks; Q.total_chunks = rows * c.nchunks;
+            if (tma && s.iir.tma_prog) {
+                Q.base.in_prog_start = s.iir.prog_in_start; Q.base.in_prog_len = s.iir.prog_in_len;
+                Q.base.n_epi_scale = 0; Q.base.epi_scale[0] = Q.base.epi_scale[1] = 1.0;
+            }
             if (getenv("SIGOPS_DEBUG"))
                 fprintf(stderr, "[sigops] IIR stage %zu: %s rows=%lld N=%lld M=%d W=%lld L=%lld chunks/row=%lld Wc=%lld matrix=%d\n", si,
                         tma ? "tma" : (s.iir.fast ? "cp.async" : "generic"), (long long)rows, (long long)g.n_out, s.iir.M,
@@ -893,10 +849,10 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                 const int M_ = s.iir.M;
                 const bool unitb = s.iir.unitb, fast = s.iir.fast;
                 add(KIND_IIR_MAIN, [=](cudaStream_t st) {
-                    if (warm) launch_iir_tma<IIR_WARM>(M_, unitb, grid, st, Q);
-                    else if (tma) launch_iir_tma<IIR_MAIN>(M_, unitb, grid, st, Q);
-                    else if (fast) launch_iir_fast<IIR_MAIN>(M_, unitb, grid, st, P);
-                    else launch_iir<IIR_MAIN>(M_, grid, stack_iir, st, P);
+                    if (warm) launch_iir_tma_any(LAUNCH_WARM, tprog, M_, unitb, grid, st, Q);
+                    else if (tma) launch_iir_tma_any(LAUNCH_MAIN, false, M_, unitb, grid, st, Q);
+                    else if (fast) launch_iir_cpasync(LAUNCH_MAIN, M_, unitb, grid, st, P);
+                    else launch_iir_generic(LAUNCH_MAIN, M_, grid, stack_iir, st, P);
                 });
             }
             if (c.nchunks > 1 && !warm) {
@@ -919,9 +875,9 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                     const int M_ = s.iir.M;
                     const bool unitb = s.iir.unitb, fast = s.iir.fast;
                     add(KIND_IIR_FIX, [=](cudaStream_t st) {
-                        if (tma) launch_iir_tma<IIR_FIX>(M_, unitb, grid, st, Q);
-                        else if (fast) launch_iir_fast<IIR_FIX>(M_, unitb, grid, st, P);
-                        else launch_iir<IIR_FIX>(M_, grid, stack_iir, st, P);
+                        if (tma) launch_iir_tma_any(LAUNCH_FIX, false, M_, unitb, grid, st, Q);
+                        else if (fast) launch_iir_cpasync(LAUNCH_FIX, M_, unitb, grid, st, P);
+                        else launch_iir_generic(LAUNCH_FIX, M_, grid, stack_iir, st, P);
                     });
                 }
             }
