@@ -67,15 +67,15 @@ __device__ __forceinline__ double gen_value(const sigops_instr& I, int64_t k) {
     return apply_fn(I.fn, t + I.d2, I.d3, I.d4);
 }
 
-__device__ __forceinline__ double leaf_value(const sigops_instr& I, const Env& env,
-                                             const double* leafconst, int pc,
-                                             int64_t n, int c, double stageval) {
+// Per-frame evaluation of the leaves that have no vector fast path (padded / non-Float64
+// buffers, channel sums, non-sinusoidal generators, frames inside a ramp).  Deliberately not
+// inlined: the 64-bit divisions and libm calls in here would otherwise be replicated V times
+// at every call site and push the kernels out of the instruction cache.
+static __device__ __noinline__ double leaf_value_slow(const sigops_instr* Ip, const BufRef* bufs, int64_t n, int c) {
+    const sigops_instr& I = *Ip;
     switch (I.leaf) {
-        case SIGOPS_LEAF_CONST:
-        case SIGOPS_LEAF_RMS:
-            return leafconst[pc];
         case SIGOPS_LEAF_BUF: {
-            const BufRef b = env.bufs[I.buf];
+            const BufRef b = bufs[I.buf];
             int64_t idx = n + I.i0;
             const int pad = (I.flags >> 1) & 3;
             if (idx < 0 || idx >= I.i1) {
@@ -90,7 +90,7 @@ __device__ __forceinline__ double leaf_value(const sigops_instr& I, const Env& e
             return load_elem(b.ptr, b.dtype, (int64_t)ch * b.ld + idx);
         }
         case SIGOPS_LEAF_CHANSUM: {
-            const BufRef b = env.bufs[I.buf];
+            const BufRef b = bufs[I.buf];
             const int64_t idx = n + I.i0;
             if (idx < 0 || idx >= I.i1) return I.d0;
             double s = load_elem(b.ptr, b.dtype, idx);
@@ -109,8 +109,6 @@ __device__ __forceinline__ double leaf_value(const sigops_instr& I, const Env& e
             if (k <= I.i1) return 1.0;
             return apply_fn(I.fn, 1.0 - (double)(k - I.i1) / (double)I.i2, 0.0, 0.0);
         }
-        case SIGOPS_LEAF_STAGE:
-            return stageval;
     }
     return 0.0;
 }
@@ -131,18 +129,24 @@ __device__ __forceinline__ void gen_trig_values(const sigops_instr& I, double2 r
     } else {
         sincos(t + I.d2, &s, &c);
     }
+    // cos-type generators track (cos, -sin): the same rotation then advances either pair
+    double x = s, y = c;
+    if (I.fn == SIGOPS_FN_COS || I.fn == SIGOPS_FN_AFFINE_COS) { x = c; y = -s; }
+    if (I.fn == SIGOPS_FN_SIN || I.fn == SIGOPS_FN_COS) {
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-        double v;
-        switch (I.fn) {
-            case SIGOPS_FN_SIN: v = s; break;
-            case SIGOPS_FN_COS: v = c; break;
-            case SIGOPS_FN_AFFINE_SIN: v = I.d3 * s + I.d4; break;
-            default: v = I.d3 * c + I.d4; break;
+        for (int j = 0; j < V; ++j) {
+            out[j] = x;
+            const double x2 = fma(x, rot.y, y * rot.x), y2 = fma(y, rot.y, -x * rot.x);
+            x = x2; y = y2;
         }
-        out[j] = v;
-        const double s2 = fma(s, rot.y, c * rot.x), c2 = fma(c, rot.y, -s * rot.x);
-        s = s2; c = c2;
+    } else {
+        const double a = I.d3, b = I.d4;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            out[j] = a * x + b;
+            const double x2 = fma(x, rot.y, y * rot.x), y2 = fma(y, rot.y, -x * rot.x);
+            x = x2; y = y2;
+        }
     }
 }
 
@@ -187,16 +191,12 @@ __device__ __forceinline__ double binop(int op, double a, double b) {
     }
 }
 
-// Evaluate a program for V samples n[j] = n0 + j*nstride of channel c (nstride must be
-// the stride prepare_program was given).  `stack` is this thread's spill area, laid out
-// [depth][V] with stride `sstride` doubles between consecutive slots (so neighbouring
-// threads interleave and stay bank-conflict free).
 // V frames of a buffer leaf, `nstride` apart.  The common case (Float64, every frame
 // inside the valid range) is V plain loads off one base pointer; everything else falls
 // back to the per-frame path (pads, other sample types).
 template <int V>
-__device__ __forceinline__ void buf_values(const sigops_instr& I, const Env& env, int64_t n0, int64_t nstride,
-                                           int c, double* out) {
+__device__ __forceinline__ void buf_values(const sigops_instr& I, const sigops_instr* Ip, const Env& env, int64_t n0,
+                                           int64_t nstride, int c, double* out) {
     const BufRef b = env.bufs[I.buf];
     const int64_t idx0 = n0 + I.i0;
     const int ch = c * I.c_mul + I.c_off;
@@ -206,21 +206,8 @@ __device__ __forceinline__ void buf_values(const sigops_instr& I, const Env& env
         for (int j = 0; j < V; ++j) out[j] = __ldg(p + j * nstride);
         return;
     }
-    const int pad = (I.flags >> 1) & 3;
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-        int64_t idx = idx0 + j * nstride;
-        bool use_pad = false;
-        if (idx < 0 || idx >= I.i1) {
-            if (pad == SIGOPS_PAD_CONST || idx < 0 || I.i1 <= 0) use_pad = true;
-            else if (pad == SIGOPS_PAD_CYCLE) idx = idx % I.i1;
-            else if (pad == SIGOPS_PAD_MIRROR) {
-                const int64_t cnt = idx / I.i1, rem = idx % I.i1;
-                idx = (cnt & 1) ? (I.i1 - 1 - rem) : rem;
-            } else idx = I.i1 - 1;
-        }
-        out[j] = use_pad ? I.d0 : load_elem(b.ptr, b.dtype, (int64_t)ch * b.ld + idx);
-    }
+    for (int j = 0; j < V; ++j) out[j] = leaf_value_slow(Ip, env.bufs, n0 + j * nstride, c);
 }
 
 // Evaluate a program for V samples n[j] = n0 + j*nstride of channel c (nstride must be
@@ -250,7 +237,7 @@ __device__ __forceinline__ void eval_program(const sigops_instr* sprog, const do
                     break;
                 }
                 case SIGOPS_LEAF_BUF:
-                    buf_values<V>(I, env, n0, nstride, c, v);
+                    buf_values<V>(I, &sprog[pc], env, n0, nstride, c, v);
                     break;
                 case SIGOPS_LEAF_STAGE:
 #pragma unroll
@@ -262,10 +249,19 @@ __device__ __forceinline__ void eval_program(const sigops_instr* sprog, const do
                         break;
                     }
                     // fall through
-                default:
+                default: {
+                    // ramps are 1 outside a short region: decide once for the V frames
+                    bool ones = false;
+                    if (I.leaf == SIGOPS_LEAF_RAMP_ON) ones = n0 + I.i0 > I.i1;
+                    else if (I.leaf == SIGOPS_LEAF_RAMP_OFF) ones = n0 + (V - 1) * nstride + I.i0 <= I.i1;
+                    if (ones) {
 #pragma unroll
-                    for (int j = 0; j < V; ++j)
-                        v[j] = leaf_value(I, env, leafconst, pc, n0 + j * nstride, c, stageval ? stageval[j] : 0.0);
+                        for (int j = 0; j < V; ++j) v[j] = 1.0;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < V; ++j) v[j] = leaf_value_slow(&sprog[pc], env.bufs, n0 + j * nstride, c);
+                    }
+                }
             }
             switch (op) {
                 case SIGOPS_OP_LOAD:

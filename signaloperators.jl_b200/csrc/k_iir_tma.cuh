@@ -72,10 +72,11 @@ struct TmaProg {
 };
 
 // 16 frames (one third of a stage) through the cascade; see cascade_tile in k_iir.cuh.
-// Returns sum(out^2) of the 16 outputs.  n0 = signal frame of p[0], c = channel (PROG only).
+// Returns sum(out^2) of the 16 outputs.  n0 = signal frame of p[0], c = channel, keep = the
+// outputs will be stored (PROG only).
 template <int M, bool ZERO_IN, bool UNITB, bool PROG>
 __device__ __forceinline__ double cascade16(Cascade<M>& f, double* p, double gain, double sc,
-                                            const TmaProg& T, int64_t n0, int c) {
+                                            const TmaProg& T, int64_t n0, int c, bool keep = true) {
     double xr[16];
 #pragma unroll
     for (int k = 0; k < 16; k += 2) {
@@ -102,7 +103,7 @@ __device__ __forceinline__ double cascade16(Cascade<M>& f, double* p, double gai
             }
         }
     }
-    if (PROG && T.ep_len > 0) {
+    if (PROG && T.ep_len > 0 && keep) {      // warm-up outputs are discarded: no epilogue
         double t[16];
         Env env{nullptr, nullptr};
         eval_program<16>(T.ep_prog, T.ep_lc, T.ep_rot, T.ep_len, env, n0, 1, c, out, t, nullptr, 0);
@@ -243,7 +244,7 @@ k_iir_tma(const __grid_constant__ IirTmaParams Q) {
         if (PROG) {          // the interpreter is big: keep one copy of it (all three blocks in one loop)
 #pragma unroll 1
             for (int q = 0; q < kStageCols; q += 16)
-                s4 += cascade16<M, MODE == IIR_FIX, UNITB, PROG>(f, buf + q, P.gain, sc, T, nstage0 + q, c);
+                s4 += cascade16<M, MODE == IIR_FIX, UNITB, PROG>(f, buf + q, P.gain, sc, T, nstage0 + q, c, off >= skip_frames);
         } else {
 #pragma unroll
             for (int q = 16; q < kStageCols; q += 16)
