@@ -26,6 +26,7 @@
 #include "launchers.h"
 #include "k_iir_carry.cuh"
 #include "k_fir.cuh"
+#include "k_fir_mma.cuh"
 #include "k_map.cuh"
 
 static_assert(sizeof(sigops_instr) == 80, "ABI: sigops_instr");
@@ -150,6 +151,7 @@ struct FirDerived {
     std::vector<double> phi;
     int dpad = 0, pmax = 0;      // window shift inside 8 outputs; positions of a 64-output tile
     int pmax32 = 0;              // positions of a 32-output tile
+    int ring32 = 0;              // k_fir_mma: positions resident while a tile is multiplied and the next two are loaded
     int in_buf = -1;
     int64_t in_len = 0;
 };
@@ -377,6 +379,7 @@ void derive_iir(sigops_plan& p, StageRT& s, int idx) {
 }
 
 constexpr size_t kFirSmemLimit = 200 * 1024;
+constexpr size_t kFirMmaSmemLimit = 220 * 1024;
 constexpr int kFirT = 64;     // table padding granularity (largest tile)
 
 // k_fir<G> geometry: merged-tap rows, window pitch and dynamic shared memory
@@ -474,6 +477,15 @@ void derive_fir(sigops_plan& p, StageRT& s, int idx) {
     s.fir.dpad = (int)dpad;
     s.fir.pmax = (int)(span + st.taps_per_phase);
     s.fir.pmax32 = (int)(span32 + st.taps_per_phase);
+    // k_fir_mma keeps the windows of tile t-1 (being multiplied) and tile t (being loaded) in its ring
+    int64_t ring = 0;
+    for (int64_t t = 0; t * kFmT < padded; ++t) {
+        const int64_t tn = (t + 2) * kFmT <= padded ? t + 1 : t;      // loads run up to one tile ahead
+        const int64_t need = (s.fir.xi0[tn * kFmT + kFmT - 1] + 2) & ~int64_t(1);
+        const int64_t p0 = (s.fir.xi0[(t > 0 ? t - 1 : 0) * kFmT] - st.taps_per_phase + 1) & ~int64_t(1);
+        ring = std::max(ring, need - p0);
+    }
+    s.fir.ring32 = (int)std::min<int64_t>(ring, 1 << 30);
     if (fir_smem_bytes(s.fir, st.taps_per_phase, 1, SIGOPS_MAX_STACK) > kFirSmemLimit)
         fail(SIGOPS_ERR_UNSUPPORTED, "%s: resampling ratio %g with %d taps/phase needs %zu bytes of shared memory per block",
              what, st.rate, st.taps_per_phase, fir_smem_bytes(s.fir, st.taps_per_phase, 1, SIGOPS_MAX_STACK));
@@ -895,6 +907,73 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
             P.pfb = pd.blob + p.tables[g.pfb_table].offset;
             P.dpfb = g.dpfb_table >= 0 ? pd.blob + p.tables[g.dpfb_table].offset : nullptr;
             P.xi0 = pd.xi0[si]; P.phi = pd.phi[si];
+            // Tensor-core path: plain Float64 rows on 16-byte boundaries, no epilogue program
+            bool mma = g.epi_prog_len == 0 && !getenv("SIGOPS_NO_FIR_MMA") &&
+                       p.bufs[s.fir.in_buf].dtype == SIGOPS_F64 && p.bufs[g.out_buf].dtype == SIGOPS_F64;
+            for (int64_t i = 0; i < ninst && mma; ++i)
+                for (int b : {s.fir.in_buf, (int)g.out_buf}) {
+                    const BufRef& rb = ((const BufRef*)slot.last_table.data())[i * nbuf + b];
+                    if (((uintptr_t)rb.ptr & 15) || (rb.nch > 1 && (rb.ld & 1)) || rb.dtype != SIGOPS_F64) mma = false;
+                }
+            if (mma) {
+                FirMmaParams Q{};
+                Q.bufrefs = d_refs; Q.scalars = scalars; Q.nbuf = nbuf; Q.nscalars = nscal;
+                Q.in_buf = s.fir.in_buf; Q.out_buf = g.out_buf; Q.sumsq_slot = g.sumsq_slot;
+                Q.in_len = s.fir.in_len; Q.nch = g.nchannels; Q.nrows = rows; Q.n_out = g.n_out;
+                Q.tapsper = g.taps_per_phase;
+                Q.ks = (int)round_up(s.fir.dpad + g.taps_per_phase, 4);
+                Q.ring = s.fir.ring32;
+                Q.pitch = Q.ring + ((4 - Q.ring % 16) + 16) % 16;
+                Q.pfb = P.pfb; Q.dpfb = P.dpfb; Q.xi0 = P.xi0; Q.phi = P.phi;
+                Q.ntiles = (g.n_out + kFmT - 1) / kFmT;
+                // both polyphase banks ride along in shared memory when that leaves the ring its room
+                const int64_t tabd = (int64_t)g.n_phases * g.taps_per_phase;
+                const size_t tab_bytes = (size_t)tabd * 8 * (P.dpfb ? 2 : 1);
+                Q.tab_doubles = tab_bytes <= 48 * 1024 ? (int)tabd : 0;
+                auto smem_for = [&](int MF) {
+                    return (size_t)8 * MF * Q.pitch * 8 + (size_t)2 * 4 * Q.ks * kFmHbPitch * 8 + (Q.tab_doubles ? tab_bytes : 0);
+                };
+                int MF = rows > 64 ? 16 : (rows > 32 ? 8 : 4);
+                if (const char* e = getenv("SIGOPS_FIR_MF")) MF = atoi(e) >= 16 ? 16 : (atoi(e) >= 8 ? 8 : 4);
+                while (MF > 4 && smem_for(MF) > kFirMmaSmemLimit) MF >>= 1;
+                const int64_t groups = (rows + 8 * MF - 1) / (8 * MF);
+                if (smem_for(MF) <= kFirMmaSmemLimit && groups <= 65535) {
+                    // segments along the time axis: whole waves of one block per SM; a segment pays
+                    // about three tiles of start-up (first window, pipeline fill)
+                    int64_t best_tps = Q.ntiles;
+                    double best_cost = 1e300;
+                    for (int w = 1; w <= 8; ++w) {
+                        int64_t nseg = std::max<int64_t>(1, std::min<int64_t>(Q.ntiles, ((int64_t)w * dev.sm_count + groups - 1) / groups));
+                        const int64_t tps = (Q.ntiles + nseg - 1) / nseg;
+                        nseg = (Q.ntiles + tps - 1) / tps;
+                        const int64_t waves = (groups * nseg + dev.sm_count - 1) / dev.sm_count;
+                        const double cost = (double)waves * (double)(tps + 3);
+                        if (cost < best_cost) { best_cost = cost; best_tps = tps; }
+                    }
+                    if (const char* e = getenv("SIGOPS_FIR_TPS")) best_tps = std::max<int64_t>(1, atoll(e));
+                    Q.tiles_per_seg = best_tps;
+                    const int64_t nseg = (Q.ntiles + best_tps - 1) / best_tps;
+                    const size_t smem = smem_for(MF);
+                    dim3 grid((unsigned)nseg, (unsigned)groups);
+                    if (getenv("SIGOPS_DEBUG"))
+                        fprintf(stderr, "[sigops] FIR stage %zu: mma rows=%lld n_out=%lld taps=%d ks=%d ring=%d pitch=%d MF=%d grid=%lldx%lld tiles/seg=%lld smem=%zu\n",
+                                si, (long long)rows, (long long)g.n_out, Q.tapsper, Q.ks, Q.ring, Q.pitch, MF, (long long)nseg,
+                                (long long)groups, (long long)best_tps, smem);
+                    add(KIND_FIR, [=](cudaStream_t st) {
+                        if (MF == 16) {
+                            ensure_dyn_smem(k_fir_mma<16>, smem);
+                            k_fir_mma<16><<<grid, kFmThreads, smem, st>>>(Q);
+                        } else if (MF == 8) {
+                            ensure_dyn_smem(k_fir_mma<8>, smem);
+                            k_fir_mma<8><<<grid, kFmThreads, smem, st>>>(Q);
+                        } else {
+                            ensure_dyn_smem(k_fir_mma<4>, smem);
+                            k_fir_mma<4><<<grid, kFmThreads, smem, st>>>(Q);
+                        }
+                    });
+                    continue;
+                }
+            }
             // rows per thread: as many as fit in shared memory, but no more than the batch can fill
             int G = 4;
             if (const char* e = getenv("SIGOPS_FIR_G")) G = std::max(1, std::min(4, atoi(e)));
@@ -1047,8 +1126,11 @@ void run_host_on_device(sigops_plan& p, int di, int64_t i_begin, int64_t i_end, 
         const size_t budget = p.ctx->ws_budget / 2;
         int64_t wave = ninst;
         auto need_for = [&](int64_t w) { return wave_workspace_bytes(p, w, dev.sm_count) + io_bytes * w + (size_t)w * (nin + nout) * sizeof(sigops_buffer); };
-        // at least 4 waves when the batch allows it, so copies overlap compute
-        if (ninst >= 8) wave = (ninst + 3) / 4;
+        // several waves when the batch allows it, so H2D of wave k+1 and D2H of wave k-1 overlap
+        // the kernels of wave k (the first H2D and last D2H are exposed: 1/nwaves of the copy time)
+        int nwaves = 16;
+        if (const char* e = getenv("SIGOPS_HOST_WAVES")) nwaves = std::max(1, atoi(e));
+        if (ninst >= 2 * nwaves) wave = (ninst + nwaves - 1) / nwaves;
         while (wave > 1 && need_for(wave) > budget) wave = (wave + 1) / 2;
         for (int s = 0; s < 2; ++s) {
             Slot& slot = dev.slots[s];
