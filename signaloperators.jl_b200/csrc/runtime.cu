@@ -149,6 +149,8 @@ struct IirDerived {
 struct FirDerived {
     std::vector<int64_t> xi0;
     std::vector<double> phi;
+    std::vector<int32_t> poff;   // k_fir_mma: (phase index - 1) * taps_per_phase
+    std::vector<double> alpha;   //            fractional phase
     int dpad = 0, pmax = 0;      // window shift inside 8 outputs; positions of a 64-output tile
     int pmax32 = 0;              // positions of a 32-output tile
     int ring32 = 0;              // k_fir_mma: positions resident while a tile is multiplied and the next two are loaded
@@ -168,6 +170,8 @@ struct PlanDev {               // device-resident constants of a plan
     double* blob = nullptr;
     std::vector<int64_t*> xi0;  // per stage
     std::vector<double*> phi;
+    std::vector<int32_t*> poff;
+    std::vector<double*> alpha;
 };
 
 }  // namespace
@@ -469,6 +473,15 @@ void derive_fir(sigops_plan& p, StageRT& s, int idx) {
         s.fir.xi0[m] = nout ? s.fir.xi0[nout - 1] : 0;
         s.fir.phi[m] = 1.0;
     }
+    // the tensor-core kernel takes the phase split into bank row and fraction (same arithmetic as
+    // k_fir.cuh: fl = floor(phi), alpha = phi - fl), so its helper warps need no FP64 instruction
+    s.fir.poff.resize(padded);
+    s.fir.alpha.resize(padded);
+    for (int64_t m = 0; m < padded; ++m) {
+        const double fl = std::floor(s.fir.phi[m]);
+        s.fir.poff[m] = (int32_t)(((int64_t)fl - 1) * st.taps_per_phase);
+        s.fir.alpha[m] = s.fir.phi[m] - fl;
+    }
     int64_t dpad = 0, span = 0;
     for (int64_t m = 0; m + kFirR - 1 < padded; ++m) dpad = std::max(dpad, s.fir.xi0[m + kFirR - 1] - s.fir.xi0[m]);
     for (int64_t m = 0; m < padded; m += kFirT) span = std::max(span, s.fir.xi0[m + kFirT - 1] - s.fir.xi0[m]);
@@ -582,6 +595,8 @@ void ensure_plan_dev(sigops_plan& p, int di) {
     }
     d.xi0.assign(p.stages.size(), nullptr);
     d.phi.assign(p.stages.size(), nullptr);
+    d.poff.assign(p.stages.size(), nullptr);
+    d.alpha.assign(p.stages.size(), nullptr);
     for (size_t i = 0; i < p.stages.size(); ++i) {
         const FirDerived& f = p.stages[i].fir;
         if (p.stages[i].st.kind != SIGOPS_STAGE_FIR) continue;
@@ -589,6 +604,10 @@ void ensure_plan_dev(sigops_plan& p, int di) {
         CUDA_OK(cudaMalloc(&d.phi[i], f.phi.size() * sizeof(double)));
         CUDA_OK(cudaMemcpy(d.xi0[i], f.xi0.data(), f.xi0.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
         CUDA_OK(cudaMemcpy(d.phi[i], f.phi.data(), f.phi.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&d.poff[i], f.poff.size() * sizeof(int32_t)));
+        CUDA_OK(cudaMalloc(&d.alpha[i], f.alpha.size() * sizeof(double)));
+        CUDA_OK(cudaMemcpy(d.poff[i], f.poff.data(), f.poff.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(d.alpha[i], f.alpha.data(), f.alpha.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
     d.ready = true;
 }
@@ -602,6 +621,8 @@ void free_plan_dev(sigops_plan& p) {
         cudaFree(d.blob);
         for (auto q : d.xi0) cudaFree(q);
         for (auto q : d.phi) cudaFree(q);
+        for (auto q : d.poff) cudaFree(q);
+        for (auto q : d.alpha) cudaFree(q);
         d.ready = false;
     }
 }
@@ -924,20 +945,24 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                 Q.ks = (int)round_up(s.fir.dpad + g.taps_per_phase, 4);
                 Q.ring = s.fir.ring32;
                 Q.pitch = Q.ring + ((4 - Q.ring % 16) + 16) % 16;
-                Q.pfb = P.pfb; Q.dpfb = P.dpfb; Q.xi0 = P.xi0; Q.phi = P.phi;
+                Q.pfb = P.pfb; Q.dpfb = P.dpfb; Q.xi0 = P.xi0; Q.poff = pd.poff[si]; Q.alpha = pd.alpha[si];
                 Q.ntiles = (g.n_out + kFmT - 1) / kFmT;
                 // both polyphase banks ride along in shared memory when that leaves the ring its room
                 const int64_t tabd = (int64_t)g.n_phases * g.taps_per_phase;
                 const size_t tab_bytes = (size_t)tabd * 8 * (P.dpfb ? 2 : 1);
-                Q.tab_doubles = tab_bytes <= 48 * 1024 ? (int)tabd : 0;
-                auto smem_for = [&](int MF) {
-                    return (size_t)8 * MF * Q.pitch * 8 + (size_t)2 * 4 * Q.ks * kFmHbPitch * 8 + (Q.tab_doubles ? tab_bytes : 0);
+                Q.tab_doubles = (int)tabd;
+                if (tab_bytes > 48 * 1024) mma = false;      // banks too large to ride along in shared memory
+                auto smem_for = [&](int RBx) {
+                    return (size_t)RBx * Q.pitch * 8 + (size_t)2 * 4 * Q.ks * kFmHbPitch * 8 + tab_bytes;
                 };
-                int MF = rows > 64 ? 16 : (rows > 32 ? 8 : 4);
-                if (const char* e = getenv("SIGOPS_FIR_MF")) MF = atoi(e) >= 16 ? 16 : (atoi(e) >= 8 ? 8 : 4);
-                while (MF > 4 && smem_for(MF) > kFirMmaSmemLimit) MF >>= 1;
-                const int64_t groups = (rows + 8 * MF - 1) / (8 * MF);
-                if (smem_for(MF) <= kFirMmaSmemLimit && groups <= 65535) {
+                // rows per block RB: as many as the batch fills and shared memory holds
+                int RB = rows > 64 ? 128 : (rows > 32 ? 64 : 32);
+                if (const char* e = getenv("SIGOPS_FIR_RB")) RB = atoi(e) >= 128 ? 128 : (atoi(e) >= 64 ? 64 : 32);
+                while (RB > 32 && smem_for(RB) > kFirMmaSmemLimit) RB >>= 1;
+                const int RH = getenv("SIGOPS_FIR_RH") ? std::max(1, std::min(2, atoi(getenv("SIGOPS_FIR_RH")))) : 2;
+                const int MF = RB;      // (kept for the debug line)
+                const int64_t groups = (rows + RB - 1) / RB;
+                if (mma && smem_for(RB) <= kFirMmaSmemLimit && groups <= 65535) {
                     // segments along the time axis: whole waves of one block per SM; a segment pays
                     // about three tiles of start-up (first window, pipeline fill)
                     int64_t best_tps = Q.ntiles;
@@ -953,23 +978,47 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                     if (const char* e = getenv("SIGOPS_FIR_TPS")) best_tps = std::max<int64_t>(1, atoll(e));
                     Q.tiles_per_seg = best_tps;
                     const int64_t nseg = (Q.ntiles + best_tps - 1) / best_tps;
-                    const size_t smem = smem_for(MF);
+                    const size_t smem = smem_for(RB);
                     dim3 grid((unsigned)nseg, (unsigned)groups);
                     if (getenv("SIGOPS_DEBUG"))
-                        fprintf(stderr, "[sigops] FIR stage %zu: mma rows=%lld n_out=%lld taps=%d ks=%d ring=%d pitch=%d MF=%d grid=%lldx%lld tiles/seg=%lld smem=%zu\n",
+                        fprintf(stderr, "[sigops] FIR stage %zu: mma rows=%lld n_out=%lld taps=%d ks=%d ring=%d pitch=%d rows/block=%d grid=%lldx%lld tiles/seg=%lld smem=%zu\n",
                                 si, (long long)rows, (long long)g.n_out, Q.tapsper, Q.ks, Q.ring, Q.pitch, MF, (long long)nseg,
                                 (long long)groups, (long long)best_tps, smem);
-                    add(KIND_FIR, [=](cudaStream_t st) {
-                        if (MF == 16) {
-                            ensure_dyn_smem(k_fir_mma<16>, smem);
-                            k_fir_mma<16><<<grid, kFmThreads, smem, st>>>(Q);
-                        } else if (MF == 8) {
-                            ensure_dyn_smem(k_fir_mma<8>, smem);
-                            k_fir_mma<8><<<grid, kFmThreads, smem, st>>>(Q);
-                        } else {
-                            ensure_dyn_smem(k_fir_mma<4>, smem);
-                            k_fir_mma<4><<<grid, kFmThreads, smem, st>>>(Q);
+                    if (getenv("SIGOPS_FIR_DBG")) {
+                        // tuning aid: one synchronous launch with cycle counters, printed per role
+                        const size_t nb = (size_t)nseg * groups;
+                        long long* dbg = nullptr;
+                        CUDA_OK(cudaMalloc(&dbg, nb * 8 * sizeof(long long)));
+                        CUDA_OK(cudaMemset(dbg, 0, nb * 8 * sizeof(long long)));
+                        FirMmaParams D = Q;
+                        D.dbg = dbg;
+                        if (RB == 128 && RH == 2) {
+                            ensure_dyn_smem(k_fir_mma<8, 2>, smem);
+                            k_fir_mma<8, 2><<<grid, 16 * 32, smem, stream>>>(D);
+                        } else if (RB == 128) {
+                            ensure_dyn_smem(k_fir_mma<16, 1>, smem);
+                            k_fir_mma<16, 1><<<grid, 8 * 32, smem, stream>>>(D);
                         }
+                        CUDA_OK(cudaStreamSynchronize(stream));
+                        std::vector<long long> h(nb * 8);
+                        CUDA_OK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+                        cudaFree(dbg);
+                        double sum[8] = {0};
+                        for (size_t b = 0; b < nb; ++b)
+                            for (int k = 0; k < 8; ++k) sum[k] += (double)h[b * 8 + k];
+                        const double per = 1.0 / ((double)nb * (double)best_tps);
+                        fprintf(stderr, "[sigops] FIR cycles/tile  aux: wait_done %.0f extend %.0f taps %.0f | compute: wait_taps %.0f wait_data %.0f dmma %.0f store %.0f\n",
+                                sum[0] * per, sum[1] * per, sum[2] * per, sum[3] * per, sum[4] * per, sum[5] * per, sum[6] * per);
+                    }
+                    add(KIND_FIR, [=](cudaStream_t st) {
+#define SIGOPS_FIR_MMA_CASE(rb, rh)                                                          \
+    if (RB == rb && RH == rh) {                                                              \
+        ensure_dyn_smem(k_fir_mma<rb / (8 * rh), rh>, smem);                                 \
+        k_fir_mma<rb / (8 * rh), rh><<<grid, 8 * rh * 32, smem, st>>>(Q);                   \
+    }
+                        SIGOPS_FIR_MMA_CASE(128, 1) SIGOPS_FIR_MMA_CASE(64, 1) SIGOPS_FIR_MMA_CASE(32, 1)
+                        SIGOPS_FIR_MMA_CASE(128, 2) SIGOPS_FIR_MMA_CASE(64, 2) SIGOPS_FIR_MMA_CASE(32, 2)
+#undef SIGOPS_FIR_MMA_CASE
                     });
                     continue;
                 }
