@@ -1,0 +1,207 @@
+// K3 (fastest path) — biquad cascades fed by 2-D tensor-map TMA.
+//
+// Same arithmetic and the same WARM decomposition as k_iir_tma.cuh (chunk k >= 1 starts Wc
+// frames early from zero state and discards those outputs; DSP.jl `filt!(DF2TFilter{SOS})`
+// reached from src/filters.jl:252-255).  What changes is who moves the data.  In k_iir_tma
+// every lane issues its own bulk copies — measured, those two instructions and the scalar
+// code around them are 40 % of the kernel's stall samples.  Here the 32 lanes of a warp are
+// 32 consecutive ROWS (a row = one channel of one instance) working on the SAME time chunk, so
+// a stage of the warp is a rectangular box of the [rows][frames] matrix and moves with ONE
+// elected-lane instruction:
+//     cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes   (load)
+//     cp.async.bulk.tensor.3d.global.shared::cta.bulk_group                          (store)
+// The matrix is described as [row][frame/16][16] so that the innermost extent is 128 bytes, the
+// widest the 128-byte swizzle allows; the box (16, 3, 32) is 384 contiguous bytes of each of
+// 32 rows.  With the swizzle a lane reading its own row 16 bytes at a time hits 8 different
+// bank groups per quarter warp (conflict free) without any padding.  Out-of-range coordinates are handled by the TMA unit:
+// frames past the end of the input read as zeros (the reference's zero padding), frames past
+// the end of the output and rows past the last one are clipped on store.
+//
+// Measured on B200 (config 2): 0.77-0.78 ms, the same as k_iir_tma's 0.776 ms, with a third fewer
+// instructions; neither deeper staging (4 warps x 4 stages, 6 x 3) nor L2 prefetch of longer row
+// pieces moves it, i.e. the ~5.1 TB/s both kernels reach is what HBM delivers for ~38 000
+// concurrent 384-byte streams, not an SM-side limit.  The kernel is therefore opt-in
+// (SIGOPS_TMAP=1); k_iir_tma stays the default because it takes any row layout and length.
+//
+// Eligibility (checked by the host): Float64 in/out, constant-gain epilogue, every row of the
+// wave at base + row*stride (true for staged host batches and for one batch tensor), frame
+// counts that are multiples of 16, WARM mode.
+#pragma once
+#include <cuda.h>
+
+#include "k_iir_tma.cuh"
+
+namespace sigops {
+
+constexpr int kTmSub = 16;                       // frames per box (128 bytes: the widest swizzled row)
+constexpr int kTmSubsPerStage = 3;               // 48-frame stages, like k_iir_tma
+constexpr int kTmStageCols = kTmSub * kTmSubsPerStage;
+constexpr int kTmSubBytes = 32 * kTmSub * 8;     // 4096
+constexpr int kTmStageBytes = kTmSubBytes * kTmSubsPerStage;
+constexpr size_t tm_smem_bytes(int nw, int ns) { return (size_t)nw * ns * kTmStageBytes + 1024; }   // + slack to align to 1024
+
+struct IirTmapParams {
+    const BufRef* bufrefs;
+    double* scalars;
+    int nbuf, nscalars;
+    int out_buf, sumsq_slot;
+    int nch;
+    int64_t nrows;
+    int64_t N, L, Wc;          // frames, chunk length, warm-up (both multiples of the stage)
+    int64_t cpr;               // chunks per row
+    int64_t nunits;            // row groups * cpr
+    double gain, scale;
+    double coef[kIirMaxSections][5];
+};
+
+__device__ __forceinline__ void tmap_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmap_store_3d(const CUtensorMap* tm, int c0, int c1, int c2, const void* smem_src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2),
+                 "r"(smem_u32(smem_src))
+                 : "memory");
+}
+
+// 16 frames of the lane's row through the cascade, in place in a swizzled box.  `row` points at
+// the lane's 128-byte row, `r7` = row index mod 8: 16-byte chunk j lives at chunk j ^ r7.
+// Returns sum(out^2) over the first `nvalid` outputs.
+template <int M, bool UNITB>
+__device__ __forceinline__ double cascade16_swz(Cascade<M>& f, double* row, int r7, double gain, double sc, int nvalid) {
+    double xr[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double2 v = *reinterpret_cast<const double2*>(row + 2 * (j ^ r7));
+        xr[2 * j] = v.x; xr[2 * j + 1] = v.y;
+    }
+    double pipe[M], out[16];
+#pragma unroll
+    for (int t = 0; t < 16 + M - 1; ++t) {
+#pragma unroll
+        for (int j = M - 1; j >= 0; --j) {
+            const int k = t - j;
+            if (k >= 0 && k < 16) {
+                const double in = (j == 0) ? xr[k] : pipe[j - 1];
+                pipe[j] = biquad_step<M, UNITB>(f, j, in);
+                if (j == M - 1) out[k] = (pipe[j] * gain) * sc;
+            }
+        }
+    }
+    double ss = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        *reinterpret_cast<double2*>(row + 2 * (j ^ r7)) = make_double2(out[2 * j], out[2 * j + 1]);
+        if (nvalid >= 16) {
+            ss = fma(out[2 * j], out[2 * j], ss);
+            ss = fma(out[2 * j + 1], out[2 * j + 1], ss);
+        } else {
+            if (2 * j < nvalid) ss = fma(out[2 * j], out[2 * j], ss);
+            if (2 * j + 1 < nvalid) ss = fma(out[2 * j + 1], out[2 * j + 1], ss);
+        }
+    }
+    return ss;
+}
+
+// NW warps per block, NS stages per warp (NS - 1 loads in flight while one stage is filtered).
+template <int M, bool UNITB, int NW, int NS>
+__global__ void __launch_bounds__(NW * 32, 1)
+k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUtensorMap tm_in,
+           const __grid_constant__ CUtensorMap tm_out) {
+    extern __shared__ unsigned char tm_smem_raw[];
+    __shared__ uint64_t bars[NW][NS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // 1024-byte aligned stage buffers (the swizzle pattern is a function of address bits 4-9)
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tm_smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* const stage0 = base + (size_t)warp * NS * kTmStageBytes;
+    auto stage_of = [&](int b) { return stage0 + b * kTmStageBytes; };
+
+    const int64_t unit = (int64_t)blockIdx.x * NW + warp;             // (row group, chunk)
+    if (unit >= P.nunits) return;
+    const int64_t grp = unit / P.cpr, k = unit % P.cpr;
+    const int64_t row = grp * 32 + lane;
+    const bool live = row < P.nrows;
+    const int64_t pre = k >= 1 ? P.Wc : 0;
+    int64_t len = P.N - k * P.L;
+    len = len > P.L ? P.L : len;                                       // >= 1 by construction of cpr
+    const int64_t work = len + pre;
+    const int64_t start = k * P.L - pre;                               // frame of stage 0, column 0
+    const int64_t nstage = (work + kTmStageCols - 1) / kTmStageCols;
+    const int c1 = (int)(grp * 32);
+
+    if (lane == 0) {
+        for (int b = 0; b < NS; ++b) mbar_init(&bars[warp][b], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_async_smem();
+    __syncwarp();
+
+    Cascade<M> f;
+    {
+        // same coefficient set-up as Cascade::init, from this kernel's parameter block
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            f.b0[j] = P.coef[j][0]; f.b1[j] = P.coef[j][1]; f.b2[j] = P.coef[j][2];
+            f.a1[j] = P.coef[j][3]; f.a2[j] = P.coef[j][4];
+            f.s1[j] = 0.0; f.s2[j] = 0.0;
+        }
+    }
+
+    // One tensor instruction per stage: box = (16 frames, 3 blocks of 16, 32 rows) of the
+    // [row][frame/16][16] view, i.e. 384 contiguous bytes per row.
+    auto issue_load = [&](int64_t h) {
+        if (lane == 0) {
+            const int b = (int)(h % NS);
+            mbar_expect_tx(&bars[warp][b], kTmStageBytes);
+            tmap_load_3d(stage_of(b), &tm_in, 0, (int)((start + h * kTmStageCols) / kTmSub), c1, &bars[warp][b]);
+        }
+    };
+
+    double ss = 0.0;
+    unsigned parity = 0u;
+    for (int64_t h = 0; h < NS - 1 && h < nstage; ++h) issue_load(h);
+    for (int64_t h = 0; h < nstage; ++h) {
+        const int b = (int)(h % NS);
+        mbar_wait(&bars[warp][b], (parity >> b) & 1u);
+        parity ^= 1u << b;
+        const int64_t off = h * kTmStageCols;
+        // smem box layout: [row][block][16 frames]; the 128-byte swizzle XORs the 16-byte chunk index
+        // with address bits 7-9 = (3*row + block) mod 8
+        double* rowp = reinterpret_cast<double*>(stage_of(b)) + lane * kTmStageCols;
+        const bool keep = off >= pre;                                  // pre is a multiple of the stage
+        double s3 = 0.0;
+#pragma unroll
+        for (int s = 0; s < kTmSubsPerStage; ++s) {
+            const int64_t rem = work - off - s * kTmSub;               // outputs of this block that exist
+            s3 += cascade16_swz<M, UNITB>(f, rowp + s * kTmSub, (3 * lane + s) & 7, P.gain, P.scale, rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0));
+            if (s == 0 && h + NS - 1 < nstage) {
+                // the stage filtered one iteration ago went to a tensor store: once the TMA unit has
+                // read it, refill it (issued after the first block so the wait is off the critical path)
+                if (lane == 0) bulk_wait_read_all();
+                issue_load(h + NS - 1);
+            }
+        }
+        // the stage was rewritten in place through the generic proxy; the next thing to touch it
+        // is the TMA unit (store now, or the refill two iterations on)
+        fence_async_smem();
+        __syncwarp();
+        if (keep) {
+            ss += s3;
+            if (lane == 0) {
+                // frames past N and rows past the last one are clipped by the tensor bounds
+                tmap_store_3d(&tm_out, 0, (int)((start + off) / kTmSub), c1, stage_of(b));
+                bulk_commit();
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) bulk_wait_all();
+    if (P.sumsq_slot >= 0 && live) {
+        const int64_t inst = row / P.nch;
+        atomicAdd(P.scalars + (size_t)inst * P.nscalars + P.sumsq_slot, ss);
+    }
+}
+
+}  // namespace sigops

@@ -1,0 +1,78 @@
+// Instantiations of k_iir_tmap (tensor-map TMA) and the host side of its tensor maps.
+#include "common.h"
+#include "launchers.h"
+#include "k_iir_tmap.cuh"
+
+namespace sigops {
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        cudaGetLastError();
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+template <int M, int NW, int NS>
+void launch_cfg(bool unitb, dim3 grid, cudaStream_t st, const IirTmapParams& P, const CUtensorMap& a, const CUtensorMap& b) {
+    constexpr size_t smem = tm_smem_bytes(NW, NS);
+    if (unitb) {
+        ensure_dyn_smem(k_iir_tmap<M, true, NW, NS>, smem);
+        k_iir_tmap<M, true, NW, NS><<<grid, NW * 32, smem, st>>>(P, a, b);
+    } else {
+        ensure_dyn_smem(k_iir_tmap<M, false, NW, NS>, smem);
+        k_iir_tmap<M, false, NW, NS><<<grid, NW * 32, smem, st>>>(P, a, b);
+    }
+}
+
+template <int M>
+void launch_m(bool unitb, dim3 grid, cudaStream_t st, const IirTmapParams& P, const CUtensorMap& a, const CUtensorMap& b) {
+    launch_cfg<M, kTmWarps, kTmStages>(unitb, grid, st, P, a, b);
+}
+
+}  // namespace
+
+bool iir_tmap_available() { return encode_fn() != nullptr; }
+
+// [rows][frames] Float64 matrix, row r at base + r*row_stride_bytes, described as
+// [row][frame/16][16]; box = (16, 3, 32), 128-byte swizzle.  `frames` must be a multiple of 16.
+bool iir_tmap_encode(void* out_map, void* base, int64_t frames, int64_t rows, int64_t row_stride_bytes) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn || frames % kTmSub) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)kTmSub, (cuuint64_t)(frames / kTmSub), (cuuint64_t)rows};
+    const cuuint64_t gstr[2] = {(cuuint64_t)kTmSub * 8, (cuuint64_t)row_stride_bytes};
+    const cuuint32_t box[3] = {(cuuint32_t)kTmSub, (cuuint32_t)kTmSubsPerStage, 32u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = fn((CUtensorMap*)out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+void launch_iir_tmap(int M, bool unitb, dim3 grid, cudaStream_t st, const IirTmapParams& P, const void* map_in, const void* map_out) {
+    const CUtensorMap& a = *(const CUtensorMap*)map_in;
+    const CUtensorMap& b = *(const CUtensorMap*)map_out;
+    switch (M) {
+        case 1: launch_m<1>(unitb, grid, st, P, a, b); break;
+        case 2: launch_m<2>(unitb, grid, st, P, a, b); break;
+        case 3: launch_m<3>(unitb, grid, st, P, a, b); break;
+        case 4: launch_m<4>(unitb, grid, st, P, a, b); break;
+        case 5: launch_m<5>(unitb, grid, st, P, a, b); break;
+        case 6: launch_m<6>(unitb, grid, st, P, a, b); break;
+        case 7: launch_m<7>(unitb, grid, st, P, a, b); break;
+        case 8: launch_m<8>(unitb, grid, st, P, a, b); break;
+        default: fail(SIGOPS_ERR_UNSUPPORTED, "IIR cascade of %d sections", M);
+    }
+    CUDA_OK(cudaGetLastError());
+}
+
+}  // namespace sigops

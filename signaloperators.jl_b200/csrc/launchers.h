@@ -17,4 +17,14 @@ void launch_iir_cpasync(int mode, int M, bool unitb, dim3 grid, cudaStream_t st,
 // TMA bulk-copy kernel (k_iir_tma); `prog` selects the variant with fused programs (WARM only)
 void launch_iir_tma_any(int mode, bool prog, int M, bool unitb, dim3 grid, cudaStream_t st, const IirTmaParams& Q);
 
+
+// tensor-map TMA kernel (k_iir_tmap, WARM mode, constant-gain epilogue).  The maps are opaque
+// 128-byte CUtensorMap objects (64-byte aligned) so that only one translation unit needs <cuda.h>.
+struct IirTmapParams;
+struct alignas(64) TensorMapBlob { unsigned char bytes[128]; };
+bool iir_tmap_available();
+bool iir_tmap_encode(void* out_map, void* base, int64_t frames, int64_t rows, int64_t row_stride_bytes);
+constexpr int kTmWarps = 8, kTmStages = 2;     // default shape: warps per block, stages per warp
+void launch_iir_tmap(int M, bool unitb, dim3 grid, cudaStream_t st, const IirTmapParams& P, const void* map_in, const void* map_out);
+
 }  // namespace sigops

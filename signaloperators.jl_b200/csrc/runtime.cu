@@ -27,6 +27,7 @@
 #include "k_iir_carry.cuh"
 #include "k_fir.cuh"
 #include "k_fir_mma.cuh"
+#include "k_iir_tmap.cuh"
 #include "k_map.cuh"
 
 static_assert(sizeof(sigops_instr) == 80, "ABI: sigops_instr");
@@ -835,6 +836,69 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                         const BufRef& rb = ((const BufRef*)slot.last_table.data())[i * nbuf + b];
                         if (((uintptr_t)rb.ptr & 15) || (rb.nch > 1 && (rb.ld & 1))) tma = false;
                     }
+            }
+            // Tensor-map path (opt-in, SIGOPS_TMAP=1: measured equal to the default, see k_iir_tmap.cuh):
+            // lanes = rows.  Needs every row of the wave at base + row*stride for both buffers (one batch
+            // tensor, or the library's own staging), enough rows to fill warps, and a filter that decays
+            // within a chunk (WARM).
+            if (tma && s.iir.fast && !s.iir.tma_prog && getenv("SIGOPS_TMAP") && iir_tmap_available() &&
+                (rows % 32 == 0 || rows >= 256) && rows * 32 < (int64_t(1) << 31) && g.n_out < (int64_t(1) << 30)) {
+                const BufRef* refs = (const BufRef*)slot.last_table.data();
+                auto uniform = [&](int b, char*& base, int64_t& stride) {
+                    const BufRef& r0 = refs[b];
+                    base = (char*)r0.ptr;
+                    stride = r0.ld * 8;
+                    if ((stride & 15) || r0.dtype != SIGOPS_F64) return false;
+                    for (int64_t i = 0; i < ninst; ++i) {
+                        const BufRef& rb = refs[i * nbuf + b];
+                        if (rb.ld != r0.ld || rb.nch != r0.nch || rb.dtype != SIGOPS_F64 ||
+                            (char*)rb.ptr != base + (int64_t)i * r0.nch * stride)
+                            return false;
+                    }
+                    return true;
+                };
+                char *bin = nullptr, *bout = nullptr;
+                int64_t sin_ = 0, sout = 0;
+                const int64_t W48 = round_up(std::max<int64_t>(s.iir.W, 1), kTmStageCols);
+                if (uniform(s.iir.plain_buf, bin, sin_) && uniform(g.out_buf, bout, sout) && 2 * W48 <= g.n_out) {
+                    // chunk length: whole waves of one block (8 warps = 8 units) per SM; a unit walks L + Wc frames
+                    const int64_t N = g.n_out, groups = (rows + 31) / 32;
+                    const int nw = kTmWarps;
+                    const int64_t jmax = std::max<int64_t>(1, (N + kTmStageCols - 1) / kTmStageCols);
+                    double best = 1e300;
+                    int64_t bestL = 0;
+                    for (int64_t j = W48 / kTmStageCols + 1; j <= jmax; j += std::max<int64_t>(1, jmax / 4096)) {
+                        const int64_t L = j * kTmStageCols, cpr = (N + L - 1) / L;
+                        const int64_t blocks = (groups * cpr + nw - 1) / nw;
+                        const int64_t waves = (blocks + dev.sm_count - 1) / dev.sm_count;
+                        const double cost = (double)waves * ((double)L + (cpr > 1 ? (double)W48 : 0.0) + 600.0);
+                        if (cost < best) { best = cost; bestL = L; }
+                    }
+                    if (const char* e = getenv("SIGOPS_IIR_L")) bestL = std::max<int64_t>(W48 + kTmStageCols, round_up(atoll(e), kTmStageCols));
+                    TensorMapBlob mi, mo;
+                    if (bestL > W48 && iir_tmap_encode(&mi, bin, std::min<int64_t>(s.iir.plain_len, N), rows, sin_) &&
+                        iir_tmap_encode(&mo, bout, N, rows, sout)) {
+                        IirTmapParams T{};
+                        T.bufrefs = d_refs; T.scalars = scalars; T.nbuf = nbuf; T.nscalars = nscal;
+                        T.out_buf = g.out_buf; T.sumsq_slot = g.sumsq_slot; T.nch = g.nchannels; T.nrows = rows;
+                        T.N = N; T.L = bestL; T.Wc = W48;
+                        T.cpr = (N + bestL - 1) / bestL;
+                        T.nunits = groups * T.cpr;
+                        T.gain = g.gain;
+                        T.scale = s.iir.scale[0] * s.iir.scale[1];
+                        const double* tc = p.blob.data() + p.tables[g.coef_table].offset;
+                        for (int j = 0; j < s.iir.M; ++j)
+                            for (int k = 0; k < 5; ++k) T.coef[j][k] = tc[j * 5 + k];
+                        const int M_ = s.iir.M;
+                        const bool unitb = s.iir.unitb;
+                        dim3 tgrid((unsigned)((T.nunits + nw - 1) / nw));
+                        if (getenv("SIGOPS_DEBUG"))
+                            fprintf(stderr, "[sigops] IIR stage %zu: tensor-map rows=%lld N=%lld M=%d W=%lld L=%lld chunks/row=%lld blocks=%u\n", si,
+                                    (long long)rows, (long long)N, M_, (long long)s.iir.W, (long long)T.L, (long long)T.cpr, tgrid.x);
+                        add(KIND_IIR_MAIN, [=](cudaStream_t st) { launch_iir_tmap(M_, unitb, tgrid, st, T, &mi, &mo); });
+                        continue;
+                    }
+                }
             }
             IirLaunch c = tma ? choose_iir_chunking_flat(s, rows, dev.sm_count) : choose_iir_chunking(s, rows, dev.sm_count);
             // the program-carrying TMA kernel only exists in the single-launch WARM form

@@ -1,0 +1,62 @@
+"""K3 through 2-D/3-D tensor-map TMA (csrc/k_iir_tmap.cuh, opt-in with SIGOPS_TMAP=1): same results
+as the default per-lane TMA kernel and as the oracle, including ragged row groups, inputs shorter
+than the output (zero padding comes from the tensor bounds) and a following Normpower.
+
+Reference behaviour: Filt on data signals, src/filters.jl:204-262 + DSP.jl DF2T SOS filt!."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from signalops import Amplify, Filt, Highpass, Lowpass, Normpower, Pad, Signal, Until, dB, kHz, s, sink_batch, zero
+
+pytestmark = pytest.mark.gpu
+F64_TOL = 1e-9
+
+
+def rms(a):
+    return float(np.sqrt(np.mean(np.asarray(a, dtype=np.float64) ** 2)))
+
+
+def run(gpu, chains, tmap):
+    """One wave per batch, so that the whole batch is one [rows][frames] matrix for the tensor map."""
+    saved = {k: os.environ.pop(k, None) for k in ("SIGOPS_TMAP", "SIGOPS_HOST_WAVES")}
+    try:
+        os.environ["SIGOPS_HOST_WAVES"] = "1"
+        if tmap:
+            os.environ["SIGOPS_TMAP"] = "1"
+        return sink_batch(chains, gpu)
+    finally:
+        for k, v in saved.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("ninst,nch,n", [(16, 2, 48000), (160, 2, 20000), (300, 1, 16016)])
+def test_lowpass_gain_batch(gpu, ninst, nch, n):
+    rng = np.random.default_rng(ninst)
+    xs = [rng.standard_normal((n, nch)) for _ in range(ninst)]
+    chain = lambda x: Signal(x, 48 * kHz) >> Filt(Lowpass, 4 * kHz, order=8) >> Amplify(-20 * dB)   # noqa: E731
+    a = run(gpu, [chain(x) for x in xs], tmap=True)
+    b = run(gpu, [chain(x) for x in xs], tmap=False)
+    for k in range(ninst):
+        assert a[k][0].shape == (n, nch)
+        assert np.max(np.abs(a[k][0] - b[k][0])) <= 1e-12 * rms(b[k][0])
+    for k in (0, ninst - 1):
+        want, _ = oracle.sink(chain(xs[k]))
+        assert np.max(np.abs(a[k][0] - want)) <= F64_TOL * rms(want)
+
+
+def test_padded_input_and_normpower(gpu):
+    """Input shorter than the output (Pad(zero) |> Until) and the sum of squares for Normpower."""
+    rng = np.random.default_rng(5)
+    xs = [rng.standard_normal((30000, 2)) for _ in range(32)]
+    chain = lambda x: (Signal(x, 48 * kHz) >> Pad(zero) >> Until(1 * s) >> Filt(Highpass, 1 * kHz, order=4)   # noqa: E731
+                       >> Normpower >> Amplify(-10 * dB))
+    a = run(gpu, [chain(x) for x in xs], tmap=True)
+    for k in (0, 13, 31):
+        want, _ = oracle.sink(chain(xs[k]))
+        assert a[k][0].shape == want.shape
+        assert np.max(np.abs(a[k][0] - want)) <= F64_TOL * rms(want)
