@@ -317,7 +317,7 @@ def run_gpu(args, rank, world, local_rank):
                     "matches_device_run": e2e_ok, "max_err_over_rms_vs_device_run": e2e_err,
                     "h2d_ms": st.h2d_ms, "kernels_ms": st.gpu_ms, "d2h_ms": st.d2h_ms},
             "gpu_launches": int(sum(n for _, n in prof.values())),
-            "roofline": {"bound": "hbm", "kernel": "k_iir_tma<4,WARM,unitb>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_iir_tmap<4,unitb> (tensor-map TMA, WARM decomposition)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "launch_ms": main_ms / max(main_n, 1),

@@ -1,4 +1,4 @@
-// K3 (fastest path) — biquad cascades fed by 2-D tensor-map TMA.
+// K3 (fastest path) — biquad cascades fed by tensor-map TMA.
 //
 // Same arithmetic and the same WARM decomposition as k_iir_tma.cuh (chunk k >= 1 starts Wc
 // frames early from zero state and discards those outputs; DSP.jl `filt!(DF2TFilter{SOS})`
@@ -17,11 +17,15 @@
 // frames past the end of the input read as zeros (the reference's zero padding), frames past
 // the end of the output and rows past the last one are clipped on store.
 //
-// Measured on B200 (config 2): 0.77-0.78 ms, the same as k_iir_tma's 0.776 ms, with a third fewer
-// instructions; neither deeper staging (4 warps x 4 stages, 6 x 3) nor L2 prefetch of longer row
-// pieces moves it, i.e. the ~5.1 TB/s both kernels reach is what HBM delivers for ~38 000
-// concurrent 384-byte streams, not an SM-side limit.  The kernel is therefore opt-in
-// (SIGOPS_TMAP=1); k_iir_tma stays the default because it takes any row layout and length.
+// Measured on B200 (config 2; k_iir_tma = 0.776 ms), warps x stages x frames per stage:
+//   8 x 2 x 48   0.773 ms   k_iir_tma's shape: a third fewer instructions, same time; 4 x 4 and 6 x 3
+//                           stagings and L2 prefetch of longer row pieces do not move it either — the
+//                           limit is what HBM delivers for ~38 000 concurrent 384-byte streams
+//   6 x 2 x 64   0.753 ms   longer pieces help (4-way bank conflicts from the even block count)
+//   4 x 2 x 80   0.732 ms   <- used: 640-byte pieces, 82 % of the measured copy peak
+//   4 x 2 x 112  0.837 ms,  2 x 2 x 192  1.39 ms   (too few lanes for the FP64 dependency chains)
+// One copy instruction per stage is what makes long pieces affordable; the per-lane kernel's copy
+// cost is per copy and it needs 8 warps to hide it.  SIGOPS_NO_TMAP=1 switches this kernel off.
 //
 // Eligibility (checked by the host): Float64 in/out, constant-gain epilogue, every row of the
 // wave at base + row*stride (true for staged host batches and for one batch tensor), frame
@@ -34,7 +38,12 @@
 namespace sigops {
 
 constexpr int kTmSub = 16;                       // frames per box (128 bytes: the widest swizzled row)
-constexpr int kTmSubsPerStage = 3;               // 48-frame stages, like k_iir_tma
+#ifndef TMSUBS
+#define TMSUBS 5                                 // (tuning builds override the shape with -DTMSUBS/-DTMW/-DTMS)
+#endif
+// 80-frame stages: 640 contiguous bytes per row and copy.  An odd number of blocks per row also keeps
+// the swizzle key (blocks*row + block) mod 8 different for 8 consecutive rows (4 blocks: 4-way conflicts).
+constexpr int kTmSubsPerStage = TMSUBS;
 constexpr int kTmStageCols = kTmSub * kTmSubsPerStage;
 constexpr int kTmSubBytes = 32 * kTmSub * 8;     // 4096
 constexpr int kTmStageBytes = kTmSubBytes * kTmSubsPerStage;
@@ -168,14 +177,14 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
         parity ^= 1u << b;
         const int64_t off = h * kTmStageCols;
         // smem box layout: [row][block][16 frames]; the 128-byte swizzle XORs the 16-byte chunk index
-        // with address bits 7-9 = (3*row + block) mod 8
+        // with address bits 7-9 = (blocks_per_stage*row + block) mod 8
         double* rowp = reinterpret_cast<double*>(stage_of(b)) + lane * kTmStageCols;
         const bool keep = off >= pre;                                  // pre is a multiple of the stage
         double s3 = 0.0;
 #pragma unroll
         for (int s = 0; s < kTmSubsPerStage; ++s) {
             const int64_t rem = work - off - s * kTmSub;               // outputs of this block that exist
-            s3 += cascade16_swz<M, UNITB>(f, rowp + s * kTmSub, (3 * lane + s) & 7, P.gain, P.scale, rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0));
+            s3 += cascade16_swz<M, UNITB>(f, rowp + s * kTmSub, (kTmSubsPerStage * lane + s) & 7, P.gain, P.scale, rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0));
             if (s == 0 && h + NS - 1 < nstage) {
                 // the stage filtered one iteration ago went to a tensor store: once the TMA unit has
                 // read it, refill it (issued after the first block so the wait is off the critical path)

@@ -837,11 +837,11 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                         if (((uintptr_t)rb.ptr & 15) || (rb.nch > 1 && (rb.ld & 1))) tma = false;
                     }
             }
-            // Tensor-map path (opt-in, SIGOPS_TMAP=1: measured equal to the default, see k_iir_tmap.cuh):
+            // Tensor-map path (k_iir_tmap.cuh; SIGOPS_NO_TMAP=1 switches it off):
             // lanes = rows.  Needs every row of the wave at base + row*stride for both buffers (one batch
             // tensor, or the library's own staging), enough rows to fill warps, and a filter that decays
             // within a chunk (WARM).
-            if (tma && s.iir.fast && !s.iir.tma_prog && getenv("SIGOPS_TMAP") && iir_tmap_available() &&
+            if (tma && s.iir.fast && !s.iir.tma_prog && !getenv("SIGOPS_NO_TMAP") && iir_tmap_available() &&
                 (rows % 32 == 0 || rows >= 256) && rows * 32 < (int64_t(1) << 31) && g.n_out < (int64_t(1) << 30)) {
                 const BufRef* refs = (const BufRef*)slot.last_table.data();
                 auto uniform = [&](int b, char*& base, int64_t& stride) {
@@ -859,29 +859,29 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                 };
                 char *bin = nullptr, *bout = nullptr;
                 int64_t sin_ = 0, sout = 0;
-                const int64_t W48 = round_up(std::max<int64_t>(s.iir.W, 1), kTmStageCols);
-                if (uniform(s.iir.plain_buf, bin, sin_) && uniform(g.out_buf, bout, sout) && 2 * W48 <= g.n_out) {
+                const int64_t Wst = round_up(std::max<int64_t>(s.iir.W, 1), kTmStageCols);
+                if (uniform(s.iir.plain_buf, bin, sin_) && uniform(g.out_buf, bout, sout) && 2 * Wst <= g.n_out) {
                     // chunk length: whole waves of one block (8 warps = 8 units) per SM; a unit walks L + Wc frames
                     const int64_t N = g.n_out, groups = (rows + 31) / 32;
                     const int nw = kTmWarps;
                     const int64_t jmax = std::max<int64_t>(1, (N + kTmStageCols - 1) / kTmStageCols);
                     double best = 1e300;
                     int64_t bestL = 0;
-                    for (int64_t j = W48 / kTmStageCols + 1; j <= jmax; j += std::max<int64_t>(1, jmax / 4096)) {
+                    for (int64_t j = Wst / kTmStageCols + 1; j <= jmax; j += std::max<int64_t>(1, jmax / 4096)) {
                         const int64_t L = j * kTmStageCols, cpr = (N + L - 1) / L;
                         const int64_t blocks = (groups * cpr + nw - 1) / nw;
                         const int64_t waves = (blocks + dev.sm_count - 1) / dev.sm_count;
-                        const double cost = (double)waves * ((double)L + (cpr > 1 ? (double)W48 : 0.0) + 600.0);
+                        const double cost = (double)waves * ((double)L + (cpr > 1 ? (double)Wst : 0.0) + 600.0);
                         if (cost < best) { best = cost; bestL = L; }
                     }
-                    if (const char* e = getenv("SIGOPS_IIR_L")) bestL = std::max<int64_t>(W48 + kTmStageCols, round_up(atoll(e), kTmStageCols));
+                    if (const char* e = getenv("SIGOPS_IIR_L")) bestL = std::max<int64_t>(Wst + kTmStageCols, round_up(atoll(e), kTmStageCols));
                     TensorMapBlob mi, mo;
-                    if (bestL > W48 && iir_tmap_encode(&mi, bin, std::min<int64_t>(s.iir.plain_len, N), rows, sin_) &&
+                    if (bestL > Wst && iir_tmap_encode(&mi, bin, std::min<int64_t>(s.iir.plain_len, N), rows, sin_) &&
                         iir_tmap_encode(&mo, bout, N, rows, sout)) {
                         IirTmapParams T{};
                         T.bufrefs = d_refs; T.scalars = scalars; T.nbuf = nbuf; T.nscalars = nscal;
                         T.out_buf = g.out_buf; T.sumsq_slot = g.sumsq_slot; T.nch = g.nchannels; T.nrows = rows;
-                        T.N = N; T.L = bestL; T.Wc = W48;
+                        T.N = N; T.L = bestL; T.Wc = Wst;
                         T.cpr = (N + bestL - 1) / bestL;
                         T.nunits = groups * T.cpr;
                         T.gain = g.gain;

@@ -1,4 +1,4 @@
-"""K3 through 2-D/3-D tensor-map TMA (csrc/k_iir_tmap.cuh, opt-in with SIGOPS_TMAP=1): same results
+"""K3 through 2-D/3-D tensor-map TMA (csrc/k_iir_tmap.cuh; SIGOPS_NO_TMAP=1 switches it off): same results
 as the default per-lane TMA kernel and as the oracle, including ragged row groups, inputs shorter
 than the output (zero padding comes from the tensor bounds) and a following Normpower.
 
@@ -21,11 +21,11 @@ def rms(a):
 
 def run(gpu, chains, tmap):
     """One wave per batch, so that the whole batch is one [rows][frames] matrix for the tensor map."""
-    saved = {k: os.environ.pop(k, None) for k in ("SIGOPS_TMAP", "SIGOPS_HOST_WAVES")}
+    saved = {k: os.environ.pop(k, None) for k in ("SIGOPS_NO_TMAP", "SIGOPS_HOST_WAVES")}
     try:
         os.environ["SIGOPS_HOST_WAVES"] = "1"
-        if tmap:
-            os.environ["SIGOPS_TMAP"] = "1"
+        if not tmap:
+            os.environ["SIGOPS_NO_TMAP"] = "1"
         return sink_batch(chains, gpu)
     finally:
         for k, v in saved.items():
