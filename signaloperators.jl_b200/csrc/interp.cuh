@@ -61,7 +61,8 @@ __device__ __forceinline__ double gen_value(const sigops_instr& I, int64_t k) {
     if (I.flags & SIGOPS_FLAG_HAS_OMEGA) {
         const double u = t * I.d1 + I.d2;
         if (I.fn == SIGOPS_FN_SIN) return sinpi(2.0 * u);
-        return apply_fn(I.fn, 6.283185307179586 * fmod(u, 1.0), I.d3, I.d4);
+        // u % 1.0 (truncated remainder, src/functions.jl:56) == u - trunc(u) exactly, without fmod's loop
+        return apply_fn(I.fn, 6.283185307179586 * (u - trunc(u)), I.d3, I.d4);
     }
     if (I.fn == SIGOPS_FN_SIN) return sinpi(2.0 * (t + I.d2));
     return apply_fn(I.fn, t + I.d2, I.d3, I.d4);
@@ -171,6 +172,12 @@ __device__ __forceinline__ void prepare_program(const sigops_instr* __restrict__
         if (I.leaf == SIGOPS_LEAF_CONST) v = I.d0;
         // rms = sqrt(mean(x^2)) over the whole N x C matrix, src/filters.jl:304
         else if (I.leaf == SIGOPS_LEAF_RMS) v = sqrt(env.scalars[I.buf] / I.d0);
+        if (I.leaf == SIGOPS_LEAF_CONST || I.leaf == SIGOPS_LEAF_RMS) {
+            // divisions by a block-uniform value (Normpower: x ./ rms) use its reciprocal, see div_uniform;
+            // rot.x = 0 marks divisors outside the range where that is exact
+            const double a = fabs(v);
+            rot.x = (a > 1e-150 && a < 1e150) ? 1.0 / v : 0.0;
+        }
         else if (I.leaf == SIGOPS_LEAF_GEN && gen_is_trig(I)) {
             const double w = (I.flags & SIGOPS_FLAG_HAS_OMEGA) ? I.d1 : 1.0;     // cycles per second
             double cyc = (double)nstride / I.d0 * w;                             // cycles per step
@@ -180,6 +187,15 @@ __device__ __forceinline__ void prepare_program(const sigops_instr* __restrict__
         leafconst[i] = v;
         leafrot[i] = rot;
     }
+}
+
+// a / k for a block-uniform k with r = RN(1/k): one Newton step on the residual gives the correctly
+// rounded quotient (Markstein), i.e. the same bits as the IEEE division the reference performs, for
+// 3 FP64 instructions instead of ~20.  Callers fall back to `/` when r == 0 (k tiny, huge, 0, inf, nan).
+__device__ __forceinline__ double div_uniform(double a, double k, double r) {
+    const double q = a * r;
+    const double e = fma(-k, q, a);
+    return fma(e, r, q);
 }
 
 __device__ __forceinline__ double binop(int op, double a, double b) {
@@ -232,6 +248,16 @@ __device__ __forceinline__ void eval_program(const sigops_instr* sprog, const do
                 case SIGOPS_LEAF_CONST:
                 case SIGOPS_LEAF_RMS: {
                     const double k = leafconst[pc];
+                    const double r = leafrot[pc].x;
+                    if (op == SIGOPS_OP_DIV && r != 0.0) {
+#pragma unroll
+                        for (int j = 0; j < V; ++j) {
+                            const double q = div_uniform(acc[j], k, r);
+                            // the Newton step loses its footing only when the quotient leaves the normal range
+                            acc[j] = (fabs(q) < 1e290 && (fabs(q) > 1e-290 || acc[j] == 0.0)) ? q : acc[j] / k;
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int j = 0; j < V; ++j) v[j] = k;
                     break;
@@ -246,6 +272,16 @@ __device__ __forceinline__ void eval_program(const sigops_instr* sprog, const do
                 case SIGOPS_LEAF_GEN:
                     if (V > 1 && gen_is_trig(I)) {
                         gen_trig_values<V>(I, leafrot[pc], n0 + I.i0, v);
+                        break;
+                    }
+                    if (V <= 8 && (I.fn == SIGOPS_FN_SAW || I.fn == SIGOPS_FN_IDENTITY) && (I.flags & SIGOPS_FLAG_HAS_OMEGA)) {
+                        // sawtooth / phase ramps: cheap enough to evaluate in line (the map kernel only)
+#pragma unroll
+                        for (int j = 0; j < V; ++j) {
+                            const double u = ((double)(n0 + I.i0 + j * nstride) / I.d0) * I.d1 + I.d2;
+                            const double x = 6.283185307179586 * (u - trunc(u));
+                            v[j] = I.fn == SIGOPS_FN_SAW ? x / 3.141592653589793 - 1.0 : x;
+                        }
                         break;
                     }
                     // fall through

@@ -9,9 +9,9 @@
 // a leaf of the consumer's program.
 //
 // HBM-bound: 8(k+1) bytes per output sample for k buffer leaves.
-// Layout: thread t of a 256-thread block owns frames t, t+256, ..., t+1792 of a
-// 2048-frame tile, so every warp access is a fully coalesced 256-byte row; the eight
-// frames share one decode of each program instruction.
+// Layout: a block walks an 8192-frame tile in four passes; in each, thread t owns frames
+// t, t+256, ..., t+1792 of a 2048-frame span, so every warp access is a fully coalesced
+// 256-byte row and the eight frames share one decode of each program instruction.
 #pragma once
 #include "interp.cuh"
 
@@ -19,7 +19,10 @@ namespace sigops {
 
 constexpr int kMapThreads = 256;
 constexpr int kMapV = 8;
-constexpr int kMapTile = kMapThreads * kMapV;
+constexpr int kMapSub = kMapThreads * kMapV;   // frames one pass of a block covers
+constexpr int kMapPasses = 4;                  // passes per block: the per-block set-up (program copy, folded
+                                               // constants, piece search) is paid once per 8192 frames
+constexpr int kMapTile = kMapSub * kMapPasses;  // frames per block when the launch is large
 constexpr int kMaxPieces = 64;
 constexpr int kMaxBufs = 32;
 
@@ -30,6 +33,7 @@ struct MapParams {
     int nbuf, nscalars;
     int out_buf, sumsq_slot, out_nch;
     int n_pieces;
+    int passes;                     // 2048-frame passes per block (kMapPasses, or 1 for small launches)
     sigops_piece pieces[kMaxPieces];
     int tile_prefix[kMaxPieces + 1];
 };
@@ -44,8 +48,13 @@ k_map(const __grid_constant__ MapParams P) {
     extern __shared__ double stack[];
 
     const int inst = blockIdx.z, c = blockIdx.y;
-    int p = 0;
-    while (p + 1 < P.n_pieces && (int)blockIdx.x >= P.tile_prefix[p + 1]) ++p;
+    // which piece this tile belongs to: the lanes of each warp compare one prefix each
+    int p = 0;       // = number of piece boundaries at or below this tile
+    for (int base = 1; base < P.n_pieces; base += 32) {
+        const int i = base + (threadIdx.x & 31);
+        const bool past = i < P.n_pieces && (int)blockIdx.x >= P.tile_prefix[i];
+        p += __popc(__ballot_sync(0xffffffffu, past));
+    }
     const sigops_piece pc = P.pieces[p];
     if (c < pc.ch_start || c >= pc.ch_start + pc.ch_count) return;
 
@@ -55,30 +64,32 @@ k_map(const __grid_constant__ MapParams P) {
     __syncthreads();
 
     const int64_t tile = (int64_t)blockIdx.x - P.tile_prefix[p];
-    const int64_t n0 = pc.out_start + tile * kMapTile + threadIdx.x;
     const int64_t nend = pc.out_start + pc.out_len;
-
-    double acc[kMapV];
-    eval_program<kMapV>(sprog, leafconst, leafrot, pc.prog_len, env, n0, kMapThreads, c, nullptr, acc,
-                        stack + threadIdx.x, kMapThreads);
-
     const BufRef ob = sbufs[P.out_buf];
     double ss = 0.0;
-    if (ob.dtype == SIGOPS_F64) {
-        double* op = reinterpret_cast<double*>(ob.ptr) + (int64_t)c * ob.ld + n0;
+#pragma unroll 1
+    for (int pass = 0; pass < P.passes; ++pass) {
+        const int64_t n0 = pc.out_start + (tile * P.passes + pass) * (int64_t)kMapSub + threadIdx.x;
+        if (n0 - threadIdx.x >= nend) break;
+        double acc[kMapV];
+        eval_program<kMapV>(sprog, leafconst, leafrot, pc.prog_len, env, n0, kMapThreads, c, nullptr, acc,
+                            stack + threadIdx.x, kMapThreads);
+        if (ob.dtype == SIGOPS_F64) {
+            double* op = reinterpret_cast<double*>(ob.ptr) + (int64_t)c * ob.ld + n0;
 #pragma unroll
-        for (int j = 0; j < kMapV; ++j)
-            if (n0 + (int64_t)j * kMapThreads < nend) {
-                op[j * kMapThreads] = acc[j];
-                ss = fma(acc[j], acc[j], ss);
-            }
-    } else {
+            for (int j = 0; j < kMapV; ++j)
+                if (n0 + (int64_t)j * kMapThreads < nend) {
+                    op[j * kMapThreads] = acc[j];
+                    ss = fma(acc[j], acc[j], ss);
+                }
+        } else {
 #pragma unroll
-        for (int j = 0; j < kMapV; ++j) {
-            const int64_t n = n0 + (int64_t)j * kMapThreads;
-            if (n < nend) {
-                const double v = store_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + n, acc[j]);
-                ss += v * v;
+            for (int j = 0; j < kMapV; ++j) {
+                const int64_t n = n0 + (int64_t)j * kMapThreads;
+                if (n < nend) {
+                    const double v = store_elem(ob.ptr, ob.dtype, (int64_t)c * ob.ld + n, acc[j]);
+                    ss += v * v;
+                }
             }
         }
     }

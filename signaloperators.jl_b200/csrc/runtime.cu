@@ -808,11 +808,18 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
             P.nbuf = nbuf; P.nscalars = nscal;
             P.out_buf = g.out_buf; P.sumsq_slot = g.sumsq_slot; P.out_nch = p.bufs[g.out_buf].nchannels;
             P.n_pieces = g.n_pieces;
+            // frames per block: four 2048-frame passes amortise the per-block set-up, unless that would
+            // leave the GPU with fewer than a few blocks per SM
+            int64_t subs = 0;
+            for (int k = 0; k < g.n_pieces; ++k)
+                subs += (p.pieces[g.piece_start + k].out_len + kMapSub - 1) / kMapSub * p.pieces[g.piece_start + k].ch_count;
+            P.passes = subs * ninst >= (int64_t)kMapPasses * dev.sm_count * 8 ? kMapPasses : 1;
+            const int64_t per_block = (int64_t)kMapSub * P.passes;
             int tiles = 0;
             for (int k = 0; k < g.n_pieces; ++k) {
                 P.pieces[k] = p.pieces[g.piece_start + k];
                 P.tile_prefix[k] = tiles;
-                tiles += (int)((P.pieces[k].out_len + kMapTile - 1) / kMapTile);
+                tiles += (int)((P.pieces[k].out_len + per_block - 1) / per_block);
             }
             P.tile_prefix[g.n_pieces] = tiles;
             if (tiles == 0) continue;
