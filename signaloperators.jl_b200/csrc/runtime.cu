@@ -634,13 +634,18 @@ struct IirLaunch {
     int blocks_per_row;
     int64_t L, Wc, nchunks;
     bool need_matrix;
+    double cost = 0.0;       // the flat chooser's estimate, in lane-frames
 };
 
 // Chunking for k_iir_tma: chunks are numbered over all rows jointly, so L can be chosen
-// freely (multiple of the 64-frame stage).  Cost model: a block's time is proportional to
-// the frames one lane walks (L in MAIN, min(W,L) in FIX) and blocks run in whole waves
-// of one block per SM.
-IirLaunch choose_iir_chunking_flat(const StageRT& s, int64_t rows, int sm_count) {
+// freely (multiple of the stage).  Cost model in units of one lane-frame, blocks running in whole
+// waves of one block per SM:
+//   WARM (W < L)          one launch, every lane walks L + Wc frames
+//   MAIN + CARRY + FIX    (W >= L) two passes over L frames each, plus the carry's walk along the
+//                         chunks of a row (one 2Mx2M mat-vec each, ~3 frame-times) and two more launches
+// Measured on B200 (README scene, W = 3307: WARM L = 3360 -> 0.375 ms, MAIN/CARRY/FIX L = 240 ->
+// 0.035 + 0.042 + 0.034 ms; 512 such rows: 0.735 ms vs 0.29 ms).
+IirLaunch choose_iir_chunking_flat(const StageRT& s, int64_t rows, int sm_count, bool allow_matrix = true) {
     const int64_t N = s.st.n_out;
     const int64_t W64 = round_up(std::max<int64_t>(s.iir.W, 1), kStageCols);
     const int64_t jmax = std::max<int64_t>(1, (N + kStageCols - 1) / kStageCols);
@@ -650,13 +655,13 @@ IirLaunch choose_iir_chunking_flat(const StageRT& s, int64_t rows, int sm_count)
     for (int64_t j = 1; j <= jmax; j += step) {
         const int64_t L = j * kStageCols;
         const int64_t cpr = (N + L - 1) / L;
+        const bool matrix = cpr > 1 && W64 >= L;
+        if (matrix && !allow_matrix && j + step <= jmax) continue;
         const int64_t blocks = (((rows * cpr) + 31) / 32 + kTmaWarps - 1) / kTmaWarps;
         const int64_t waves = (blocks + sm_count - 1) / sm_count;
-        const double fix = cpr > 1 ? (double)std::min(W64, L) * (W64 >= L ? 1.0 : 1.2) : 0.0;
-        double cost = (double)waves * ((double)L + fix + 600.0);      // + fixed per-wave cost (launch, pipeline fill)
-        // slow decay (W >= L): MAIN + CARRY + FIX; the carry walks the chunks of a row one after the
-        // other (one dependent 2Mx2M mat-vec per chunk, ~150 frame-times each)
-        if (cpr > 1 && W64 >= L) cost += (double)L * waves + 150.0 * (double)cpr + 1200.0;
+        double cost;
+        if (matrix) cost = (double)waves * (2.0 * (double)L + 1200.0) + 3.0 * (double)cpr + 400.0;
+        else cost = (double)waves * ((double)L + (cpr > 1 ? (double)W64 : 0.0) + 600.0);
         if (N % L) cost *= 1.02;                                     // ragged last chunk takes the scalar path
         if (cost < best) { best = cost; bestL = L; }
     }
@@ -666,7 +671,8 @@ IirLaunch choose_iir_chunking_flat(const StageRT& s, int64_t rows, int sm_count)
     r.L = bestL;
     r.nchunks = (N + bestL - 1) / bestL;
     r.Wc = std::min(W64, r.L);
-    r.need_matrix = s.iir.W >= r.L;
+    r.need_matrix = r.nchunks > 1 && s.iir.W >= r.L;
+    r.cost = best;
     return r;
 }
 
@@ -882,8 +888,14 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                         if (cost < best) { best = cost; bestL = L; }
                     }
                     if (const char* e = getenv("SIGOPS_IIR_L")) bestL = std::max<int64_t>(Wst + kTmStageCols, round_up(atoll(e), kTmStageCols));
+                    // A slowly decaying filter is better served by k_iir_tma's short chunks and carry pass.
+                    // Both estimates are in lane-frames; a lane-frame takes about max(100, 0.82 * lanes per SM)
+                    // cycles (measured: 210 with 256 lanes, 102 with 128), which makes them comparable.
+                    auto frame_cycles = [](int lanes) { return std::max(100.0, 0.82 * lanes); };
+                    const bool tmap_wins = best * frame_cycles(32 * nw) <=
+                                           choose_iir_chunking_flat(s, rows, dev.sm_count).cost * frame_cycles(32 * kTmaWarps);
                     TensorMapBlob mi, mo;
-                    if (bestL > Wst && iir_tmap_encode(&mi, bin, std::min<int64_t>(s.iir.plain_len, N), rows, sin_) &&
+                    if (bestL > Wst && tmap_wins && iir_tmap_encode(&mi, bin, std::min<int64_t>(s.iir.plain_len, N), rows, sin_) &&
                         iir_tmap_encode(&mo, bout, N, rows, sout)) {
                         IirTmapParams T{};
                         T.bufrefs = d_refs; T.scalars = scalars; T.nbuf = nbuf; T.nscalars = nscal;
@@ -907,7 +919,8 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                     }
                 }
             }
-            IirLaunch c = tma ? choose_iir_chunking_flat(s, rows, dev.sm_count) : choose_iir_chunking(s, rows, dev.sm_count);
+            // (the program-carrying TMA kernel has no MAIN/FIX form: keep it to chunkings it can run)
+            IirLaunch c = tma ? choose_iir_chunking_flat(s, rows, dev.sm_count, !s.iir.tma_prog) : choose_iir_chunking(s, rows, dev.sm_count);
             // the program-carrying TMA kernel only exists in the single-launch WARM form
             const bool tprog = tma && s.iir.tma_prog;
             if (tprog && c.need_matrix) {
