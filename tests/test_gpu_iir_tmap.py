@@ -60,3 +60,17 @@ def test_padded_input_and_normpower(gpu):
         want, _ = oracle.sink(chain(xs[k]))
         assert a[k][0].shape == want.shape
         assert np.max(np.abs(a[k][0] - want)) <= F64_TOL * rms(want)
+
+
+def test_slow_decay_batch_takes_short_chunks_and_the_carry_pass(gpu):
+    """A band-stop whose response needs ~3300 frames to die out, on a batch: the planner picks
+    MAIN + CARRY + FIX with chunks far shorter than the decay (csrc/runtime.cu cost model)."""
+    from signalops import Bandstop
+    rng = np.random.default_rng(11)
+    xs = [rng.standard_normal((44100, 2)) for _ in range(40)]
+    chain = lambda x: Signal(x, 44.1 * kHz) >> Filt(Bandstop, 0.5 * kHz, 2 * kHz) >> Normpower >> Amplify(-20 * dB)   # noqa: E731
+    got = run(gpu, [chain(x) for x in xs], tmap=True)
+    for k in (0, 21, 39):
+        want, _ = oracle.sink(chain(xs[k]))
+        assert got[k][0].shape == want.shape
+        assert np.max(np.abs(got[k][0] - want)) <= F64_TOL * rms(want)
