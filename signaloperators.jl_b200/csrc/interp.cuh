@@ -124,7 +124,7 @@ __device__ __forceinline__ void gen_trig_values(const sigops_instr& I, double2 r
     if (I.flags & SIGOPS_FLAG_HAS_OMEGA) {
         const double u = t * I.d1 + I.d2;
         if (I.fn == SIGOPS_FN_SIN) sincospi(2.0 * u, &s, &c);
-        else sincos(6.283185307179586 * fmod(u, 1.0), &s, &c);
+        else sincos(6.283185307179586 * (u - trunc(u)), &s, &c);   // u % 1.0 exactly, see gen_value
     } else if (I.fn == SIGOPS_FN_SIN) {
         sincospi(2.0 * (t + I.d2), &s, &c);
     } else {

@@ -34,6 +34,11 @@
 //     known to have passed its previous phase), `taps[t&1]` (band of tile t built),
 //     `done[t&1]` (compute warps; releases ring slots and the tap buffer two tiles later).
 //
+// Tried and dropped: staging the finished tile in shared memory and letting the aux warps write it
+// out as whole 256-byte row pieces (the fragment stores cost the compute warps ~950 cycles per tile
+// in the LSU).  It fits (tap bands at pitch 8), but the drain lengthens the aux path, which is
+// the critical one: 1.92 ms against 1.76 ms.
+//
 // Eligibility (checked by the host): Float64 in/out, 16-byte aligned rows, no epilogue
 // program (the sum of squares for a following Normpower is supported).  Everything else
 // takes k_fir.cuh.
