@@ -37,7 +37,9 @@
 // Tried and dropped: staging the finished tile in shared memory and letting the aux warps write it
 // out as whole 256-byte row pieces (the fragment stores cost the compute warps ~950 cycles per tile
 // in the LSU).  It fits (tap bands at pitch 8), but the drain lengthens the aux path, which is
-// the critical one: 1.92 ms against 1.76 ms.
+// the critical one: 1.92 ms against 1.76 ms.  Also dropped: building the B-fragment elements in the
+// compute warps (no tap buffer, no taps barrier) — per k-step it costs a pipe switch each (2.30 ms),
+// batched before the loop it is ~1000 cycles per tile that nothing overlaps (2.17 ms).
 //
 // Eligibility (checked by the host): Float64 in/out, 16-byte aligned rows, no epilogue
 // program (the sum of squares for a following Normpower is supported).  Everything else
