@@ -39,7 +39,10 @@
 // in the LSU).  It fits (tap bands at pitch 8), but the drain lengthens the aux path, which is
 // the critical one: 1.92 ms against 1.76 ms.  Also dropped: building the B-fragment elements in the
 // compute warps (no tap buffer, no taps barrier) — per k-step it costs a pipe switch each (2.30 ms),
-// batched before the loop it is ~1000 cycles per tile that nothing overlaps (2.17 ms).
+// batched before the loop it is ~1000 cycles per tile that nothing overlaps (2.17 ms).  And a single
+// lane issuing all of a warp's bulk copies in a scalar loop is slower than lane = row (~340 against
+// ~110 cycles per copy): the per-row copies are bound by the TMA unit's issue rate, which only fewer,
+// larger copies (a tensor map over all rows) would lift.
 //
 // Eligibility (checked by the host): Float64 in/out, 16-byte aligned rows, no epilogue
 // program (the sum of squares for a following Normpower is supported).  Everything else
