@@ -11,18 +11,19 @@
 //     cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes   (load)
 //     cp.async.bulk.tensor.3d.global.shared::cta.bulk_group                          (store)
 // The matrix is described as [row][frame/16][16] so that the innermost extent is 128 bytes, the
-// widest the 128-byte swizzle allows; the box (16, 3, 32) is 384 contiguous bytes of each of
+// widest the 128-byte swizzle allows; the box (16, 5, 32) is 640 contiguous bytes of each of
 // 32 rows.  With the swizzle a lane reading its own row 16 bytes at a time hits 8 different
-// bank groups per quarter warp (conflict free) without any padding.  Out-of-range coordinates are handled by the TMA unit:
-// frames past the end of the input read as zeros (the reference's zero padding), frames past
-// the end of the output and rows past the last one are clipped on store.
+// bank groups per quarter warp (conflict free) without any padding.  Out-of-range coordinates
+// are handled by the TMA unit: frames past the end of the input read as zeros (the reference's
+// zero padding), frames past the end of the output and rows past the last one are clipped on
+// store.
 //
 // Measured on B200 (config 2; k_iir_tma = 0.776 ms), warps x stages x frames per stage:
 //   8 x 2 x 48   0.773 ms   k_iir_tma's shape: a third fewer instructions, same time; 4 x 4 and 6 x 3
 //                           stagings and L2 prefetch of longer row pieces do not move it either — the
 //                           limit is what HBM delivers for ~38 000 concurrent 384-byte streams
 //   6 x 2 x 64   0.753 ms   longer pieces help (4-way bank conflicts from the even block count)
-//   4 x 2 x 80   0.732 ms   <- used: 640-byte pieces, 82 % of the measured copy peak
+//   4 x 2 x 80   0.732 ms   <- used: 640-byte pieces; 0.718 ms inside bench.py = 84 % of the measured copy peak
 //   4 x 2 x 112  0.837 ms,  2 x 2 x 192  1.39 ms   (too few lanes for the FP64 dependency chains)
 // One copy instruction per stage is what makes long pieces affordable; the per-lane kernel's copy
 // cost is per copy and it needs 8 warps to hide it.  SIGOPS_NO_TMAP=1 switches this kernel off.
