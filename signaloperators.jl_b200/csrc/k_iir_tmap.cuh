@@ -38,14 +38,14 @@
 
 namespace sigops {
 
-constexpr int kTmSub = 16;                       // frames per box (128 bytes: the widest swizzled row)
+constexpr int kTmSub = 16;                       // Float64 frames per 128-byte box row (the widest swizzled row)
 #ifndef TMSUBS
 #define TMSUBS 5                                 // (tuning builds override the shape with -DTMSUBS/-DTMW/-DTMS)
 #endif
 // 80-frame stages: 640 contiguous bytes per row and copy.  An odd number of blocks per row also keeps
 // the swizzle key (blocks*row + block) mod 8 different for 8 consecutive rows (4 blocks: 4-way conflicts).
 constexpr int kTmSubsPerStage = TMSUBS;
-constexpr int kTmStageCols = kTmSub * kTmSubsPerStage;
+constexpr int kTmStageCols = kTmSub * kTmSubsPerStage;   // Float64 frames per stage
 constexpr int kTmSubBytes = 32 * kTmSub * 8;     // 4096
 constexpr int kTmStageBytes = kTmSubBytes * kTmSubsPerStage;
 constexpr size_t tm_smem_bytes(int nw, int ns) { return (size_t)nw * ns * kTmStageBytes + 1024; }   // + slack to align to 1024
@@ -76,16 +76,27 @@ __device__ __forceinline__ void tmap_store_3d(const CUtensorMap* tm, int c0, int
                  : "memory");
 }
 
-// 16 frames of the lane's row through the cascade, in place in a swizzled box.  `row` points at
-// the lane's 128-byte row, `r7` = row index mod 8: 16-byte chunk j lives at chunk j ^ r7.
-// Returns sum(out^2) over the first `nvalid` outputs.
-template <int M, bool UNITB>
-__device__ __forceinline__ double cascade16_swz(Cascade<M>& f, double* row, int r7, double gain, double sc, int nvalid) {
+// 16 frames of the lane's row through the cascade, in place in a swizzled box.  `row` points at the
+// lane's 128-byte box row, `key` = address bits 7-9 of that row: 16-byte chunk j lives at chunk
+// j ^ key.  Float64: the row is one 16-frame block (8 chunks).  Float32: it holds two (blk = 0, 1; 4
+// chunks each); samples are widened on load, the state and all arithmetic stay Float64 like the
+// reference's DF2T filter state, and results are rounded on store.
+// Returns sum(out^2) over the first `nvalid` outputs as stored.
+template <int M, bool UNITB, class T>
+__device__ __forceinline__ double cascade16_swz(Cascade<M>& f, unsigned char* row, int key, int blk, double gain, double sc, int nvalid) {
     double xr[16];
+    if (sizeof(T) == 8) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const double2 v = *reinterpret_cast<const double2*>(row + 2 * (j ^ r7));
-        xr[2 * j] = v.x; xr[2 * j + 1] = v.y;
+        for (int j = 0; j < 8; ++j) {
+            const double2 v = *reinterpret_cast<const double2*>(row + ((j ^ key) << 4));
+            xr[2 * j] = v.x; xr[2 * j + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 v = *reinterpret_cast<const float4*>(row + (((4 * blk + j) ^ key) << 4));
+            xr[4 * j] = v.x; xr[4 * j + 1] = v.y; xr[4 * j + 2] = v.z; xr[4 * j + 3] = v.w;
+        }
     }
     double pipe[M], out[16];
 #pragma unroll
@@ -100,26 +111,31 @@ __device__ __forceinline__ double cascade16_swz(Cascade<M>& f, double* row, int 
             }
         }
     }
-    double ss = 0.0;
+    if (sizeof(T) == 8) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        *reinterpret_cast<double2*>(row + 2 * (j ^ r7)) = make_double2(out[2 * j], out[2 * j + 1]);
-        if (nvalid >= 16) {
-            ss = fma(out[2 * j], out[2 * j], ss);
-            ss = fma(out[2 * j + 1], out[2 * j + 1], ss);
-        } else {
-            if (2 * j < nvalid) ss = fma(out[2 * j], out[2 * j], ss);
-            if (2 * j + 1 < nvalid) ss = fma(out[2 * j + 1], out[2 * j + 1], ss);
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<double2*>(row + ((j ^ key) << 4)) = make_double2(out[2 * j], out[2 * j + 1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 v = make_float4((float)out[4 * j], (float)out[4 * j + 1], (float)out[4 * j + 2], (float)out[4 * j + 3]);
+            *reinterpret_cast<float4*>(row + (((4 * blk + j) ^ key) << 4)) = v;
+            out[4 * j] = v.x; out[4 * j + 1] = v.y; out[4 * j + 2] = v.z; out[4 * j + 3] = v.w;
         }
     }
+    double ss = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        if (nvalid >= 16 || k < nvalid) ss = fma(out[k], out[k], ss);
     return ss;
 }
 
 // NW warps per block, NS stages per warp (NS - 1 loads in flight while one stage is filtered).
-template <int M, bool UNITB, int NW, int NS>
+template <int M, bool UNITB, int NW, int NS, class T>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUtensorMap tm_in,
            const __grid_constant__ CUtensorMap tm_out) {
+    constexpr int SUB = 128 / (int)sizeof(T);        // frames per 128-byte box row: 16 or 32
+    constexpr int SC = SUB * kTmSubsPerStage;        // frames per stage: 80 or 160
     extern __shared__ unsigned char tm_smem_raw[];
     __shared__ uint64_t bars[NW][NS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -138,7 +154,7 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
     len = len > P.L ? P.L : len;                                       // >= 1 by construction of cpr
     const int64_t work = len + pre;
     const int64_t start = k * P.L - pre;                               // frame of stage 0, column 0
-    const int64_t nstage = (work + kTmStageCols - 1) / kTmStageCols;
+    const int64_t nstage = (work + SC - 1) / SC;
     const int c1 = (int)(grp * 32);
 
     if (lane == 0) {
@@ -159,13 +175,13 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
         }
     }
 
-    // One tensor instruction per stage: box = (16 frames, 3 blocks of 16, 32 rows) of the
-    // [row][frame/16][16] view, i.e. 384 contiguous bytes per row.
+    // One tensor instruction per stage: box = (128 bytes, 5 blocks, 32 rows) of the
+    // [row][frame/SUB][SUB] view, i.e. 640 contiguous bytes per row.
     auto issue_load = [&](int64_t h) {
         if (lane == 0) {
             const int b = (int)(h % NS);
             mbar_expect_tx(&bars[warp][b], kTmStageBytes);
-            tmap_load_3d(stage_of(b), &tm_in, 0, (int)((start + h * kTmStageCols) / kTmSub), c1, &bars[warp][b]);
+            tmap_load_3d(stage_of(b), &tm_in, 0, (int)((start + h * SC) / SUB), c1, &bars[warp][b]);
         }
     };
 
@@ -176,16 +192,20 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
         const int b = (int)(h % NS);
         mbar_wait(&bars[warp][b], (parity >> b) & 1u);
         parity ^= 1u << b;
-        const int64_t off = h * kTmStageCols;
-        // smem box layout: [row][block][16 frames]; the 128-byte swizzle XORs the 16-byte chunk index
+        const int64_t off = h * SC;
+        // smem box layout: [row][block][128 bytes]; the 128-byte swizzle XORs the 16-byte chunk index
         // with address bits 7-9 = (blocks_per_stage*row + block) mod 8
-        double* rowp = reinterpret_cast<double*>(stage_of(b)) + lane * kTmStageCols;
+        unsigned char* rowp = stage_of(b) + lane * (kTmSubsPerStage * 128);
         const bool keep = off >= pre;                                  // pre is a multiple of the stage
         double s3 = 0.0;
 #pragma unroll
         for (int s = 0; s < kTmSubsPerStage; ++s) {
-            const int64_t rem = work - off - s * kTmSub;               // outputs of this block that exist
-            s3 += cascade16_swz<M, UNITB>(f, rowp + s * kTmSub, (kTmSubsPerStage * lane + s) & 7, P.gain, P.scale, rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0));
+#pragma unroll
+            for (int blk = 0; blk < SUB / 16; ++blk) {
+                const int64_t rem = work - off - s * SUB - blk * 16;   // outputs of this block that exist
+                s3 += cascade16_swz<M, UNITB, T>(f, rowp + s * 128, (kTmSubsPerStage * lane + s) & 7, blk, P.gain, P.scale,
+                                                 rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0));
+            }
             if (s == 0 && h + NS - 1 < nstage) {
                 // the stage filtered one iteration ago went to a tensor store: once the TMA unit has
                 // read it, refill it (issued after the first block so the wait is off the critical path)
@@ -201,7 +221,7 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
             ss += s3;
             if (lane == 0) {
                 // frames past N and rows past the last one are clipped by the tensor bounds
-                tmap_store_3d(&tm_out, 0, (int)((start + off) / kTmSub), c1, stage_of(b));
+                tmap_store_3d(&tm_out, 0, (int)((start + off) / SUB), c1, stage_of(b));
                 bulk_commit();
             }
         }

@@ -22,54 +22,58 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-template <int M, int NW, int NS>
+template <int M, int NW, int NS, class T>
 void launch_cfg(bool unitb, dim3 grid, cudaStream_t st, const IirTmapParams& P, const CUtensorMap& a, const CUtensorMap& b) {
     constexpr size_t smem = tm_smem_bytes(NW, NS);
     if (unitb) {
-        ensure_dyn_smem(k_iir_tmap<M, true, NW, NS>, smem);
-        k_iir_tmap<M, true, NW, NS><<<grid, NW * 32, smem, st>>>(P, a, b);
+        ensure_dyn_smem(k_iir_tmap<M, true, NW, NS, T>, smem);
+        k_iir_tmap<M, true, NW, NS, T><<<grid, NW * 32, smem, st>>>(P, a, b);
     } else {
-        ensure_dyn_smem(k_iir_tmap<M, false, NW, NS>, smem);
-        k_iir_tmap<M, false, NW, NS><<<grid, NW * 32, smem, st>>>(P, a, b);
+        ensure_dyn_smem(k_iir_tmap<M, false, NW, NS, T>, smem);
+        k_iir_tmap<M, false, NW, NS, T><<<grid, NW * 32, smem, st>>>(P, a, b);
     }
 }
 
 template <int M>
-void launch_m(bool unitb, dim3 grid, cudaStream_t st, const IirTmapParams& P, const CUtensorMap& a, const CUtensorMap& b) {
-    launch_cfg<M, kTmWarps, kTmStages>(unitb, grid, st, P, a, b);
+void launch_m(bool f32, bool unitb, dim3 grid, cudaStream_t st, const IirTmapParams& P, const CUtensorMap& a, const CUtensorMap& b) {
+    if (f32) launch_cfg<M, kTmWarps, kTmStages, float>(unitb, grid, st, P, a, b);
+    else launch_cfg<M, kTmWarps, kTmStages, double>(unitb, grid, st, P, a, b);
 }
 
 }  // namespace
 
 bool iir_tmap_available() { return encode_fn() != nullptr; }
 
-// [rows][frames] Float64 matrix, row r at base + r*row_stride_bytes, described as
-// [row][frame/16][16]; box = (16, 3, 32), 128-byte swizzle.  `frames` must be a multiple of 16.
-bool iir_tmap_encode(void* out_map, void* base, int64_t frames, int64_t rows, int64_t row_stride_bytes) {
+// [rows][frames] matrix of Float64 (elem_bytes 8) or Float32 (4) samples, row r at
+// base + r*row_stride_bytes, described as [row][frame/S][S] with S = 128 bytes of samples;
+// box = (S, 5, 32), 128-byte swizzle.  `frames` must be a multiple of S.
+bool iir_tmap_encode(void* out_map, void* base, int64_t frames, int64_t rows, int64_t row_stride_bytes, int elem_bytes) {
     EncodeTiledFn fn = encode_fn();
-    if (!fn || frames % kTmSub) return false;
-    const cuuint64_t gdim[3] = {(cuuint64_t)kTmSub, (cuuint64_t)(frames / kTmSub), (cuuint64_t)rows};
-    const cuuint64_t gstr[2] = {(cuuint64_t)kTmSub * 8, (cuuint64_t)row_stride_bytes};
-    const cuuint32_t box[3] = {(cuuint32_t)kTmSub, (cuuint32_t)kTmSubsPerStage, 32u};
+    const int S = 128 / elem_bytes;
+    if (!fn || (elem_bytes != 4 && elem_bytes != 8) || frames % S) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)S, (cuuint64_t)(frames / S), (cuuint64_t)rows};
+    const cuuint64_t gstr[2] = {128, (cuuint64_t)row_stride_bytes};
+    const cuuint32_t box[3] = {(cuuint32_t)S, (cuuint32_t)kTmSubsPerStage, 32u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
-    const CUresult r = fn((CUtensorMap*)out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstr, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = fn((CUtensorMap*)out_map, elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base,
+                          gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
-void launch_iir_tmap(int M, bool unitb, dim3 grid, cudaStream_t st, const IirTmapParams& P, const void* map_in, const void* map_out) {
+void launch_iir_tmap(bool f32, int M, bool unitb, dim3 grid, cudaStream_t st, const IirTmapParams& P, const void* map_in,
+                     const void* map_out) {
     const CUtensorMap& a = *(const CUtensorMap*)map_in;
     const CUtensorMap& b = *(const CUtensorMap*)map_out;
     switch (M) {
-        case 1: launch_m<1>(unitb, grid, st, P, a, b); break;
-        case 2: launch_m<2>(unitb, grid, st, P, a, b); break;
-        case 3: launch_m<3>(unitb, grid, st, P, a, b); break;
-        case 4: launch_m<4>(unitb, grid, st, P, a, b); break;
-        case 5: launch_m<5>(unitb, grid, st, P, a, b); break;
-        case 6: launch_m<6>(unitb, grid, st, P, a, b); break;
-        case 7: launch_m<7>(unitb, grid, st, P, a, b); break;
-        case 8: launch_m<8>(unitb, grid, st, P, a, b); break;
+        case 1: launch_m<1>(f32, unitb, grid, st, P, a, b); break;
+        case 2: launch_m<2>(f32, unitb, grid, st, P, a, b); break;
+        case 3: launch_m<3>(f32, unitb, grid, st, P, a, b); break;
+        case 4: launch_m<4>(f32, unitb, grid, st, P, a, b); break;
+        case 5: launch_m<5>(f32, unitb, grid, st, P, a, b); break;
+        case 6: launch_m<6>(f32, unitb, grid, st, P, a, b); break;
+        case 7: launch_m<7>(f32, unitb, grid, st, P, a, b); break;
+        case 8: launch_m<8>(f32, unitb, grid, st, P, a, b); break;
         default: fail(SIGOPS_ERR_UNSUPPORTED, "IIR cascade of %d sections", M);
     }
     CUDA_OK(cudaGetLastError());

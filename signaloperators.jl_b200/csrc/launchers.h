@@ -23,12 +23,13 @@ void launch_iir_tma_any(int mode, bool prog, int M, bool unitb, dim3 grid, cudaS
 struct IirTmapParams;
 struct alignas(64) TensorMapBlob { unsigned char bytes[128]; };
 bool iir_tmap_available();
-bool iir_tmap_encode(void* out_map, void* base, int64_t frames, int64_t rows, int64_t row_stride_bytes);
+bool iir_tmap_encode(void* out_map, void* base, int64_t frames, int64_t rows, int64_t row_stride_bytes, int elem_bytes);
 #ifndef TMW
 #define TMW 4
 #define TMS 2
 #endif
 constexpr int kTmWarps = TMW, kTmStages = TMS;     // warps per block, stages per warp (160 KB of stages)
-void launch_iir_tmap(int M, bool unitb, dim3 grid, cudaStream_t st, const IirTmapParams& P, const void* map_in, const void* map_out);
+void launch_iir_tmap(bool f32, int M, bool unitb, dim3 grid, cudaStream_t st, const IirTmapParams& P, const void* map_in,
+                     const void* map_out);
 
 }  // namespace sigops

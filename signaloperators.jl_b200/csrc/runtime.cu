@@ -140,6 +140,7 @@ struct IirDerived {
     int plain_buf = -1;
     int64_t plain_len = 0;
     bool fast = false;             // k_iir_fast applies (f64 in/out, constant-gain epilogue)
+    bool fast32 = false;           // same shape on Float32 buffers: k_iir_tmap<float> applies
     bool tma_prog = false;         // k_iir_tma<PROG>: one plain f64 buffer + buffer-free programs
     int prog_in_start = 0, prog_in_len = 0;   // input program with the buffer leaf turned into LEAF_STAGE
     bool unitb = false;            // every section has b0 == 1 and b2 == 1 exactly
@@ -345,6 +346,26 @@ void derive_iir(sigops_plan& p, StageRT& s, int idx) {
     }
     s.iir.fast = epi_ok && s.iir.plain_in && p.bufs[s.iir.plain_buf].dtype == SIGOPS_F64 &&
                  p.bufs[st.out_buf].dtype == SIGOPS_F64;
+    // Float32 in and out (state and arithmetic stay Float64): the same epilogue shape, with the
+    // final rounding to Float32 that the store performs anyway
+    if (!epi_ok && st.epi_prog_len >= 2 && st.epi_prog_len <= 4 && s.iir.plain_in &&
+        p.bufs[s.iir.plain_buf].dtype == SIGOPS_F32 && p.bufs[st.out_buf].dtype == SIGOPS_F32) {
+        const sigops_instr* E = &p.instrs[st.epi_prog_start];
+        const int n = st.epi_prog_len - 1;
+        bool ok = E[0].op == SIGOPS_OP_LOAD && E[0].leaf == SIGOPS_LEAF_STAGE && E[n].op == SIGOPS_OP_CAST_F32;
+        int ns = 0;
+        double sc[2] = {1.0, 1.0};
+        for (int i = 1; i < n && ok; ++i) {
+            ok = E[i].op == SIGOPS_OP_MUL && E[i].leaf == SIGOPS_LEAF_CONST;
+            if (ok) sc[ns++] = E[i].d0;
+        }
+        if (ok) {
+            s.iir.fast32 = true;
+            s.iir.n_scale = ns;
+            s.iir.scale[0] = sc[0]; s.iir.scale[1] = sc[1];
+        }
+    } else if (epi_ok && s.iir.plain_in && p.bufs[s.iir.plain_buf].dtype == SIGOPS_F32 && p.bufs[st.out_buf].dtype == SIGOPS_F32)
+        s.iir.fast32 = true;
     // TMA + fused programs: the input program reads exactly one plain Float64 buffer, nothing else
     // in either program touches a buffer or an RMS slot
     if (!s.iir.fast && p.bufs[st.out_buf].dtype == SIGOPS_F64) {
@@ -854,17 +875,21 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
             // lanes = rows.  Needs every row of the wave at base + row*stride for both buffers (one batch
             // tensor, or the library's own staging), enough rows to fill warps, and a filter that decays
             // within a chunk (WARM).
-            if (tma && s.iir.fast && !s.iir.tma_prog && !getenv("SIGOPS_NO_TMAP") && iir_tmap_available() &&
+            const bool f32 = s.iir.fast32;
+            const int esz = f32 ? 4 : 8;
+            const int stage_cols = kTmStageCols * (f32 ? 2 : 1);
+            if (((tma && s.iir.fast && !s.iir.tma_prog) || f32) && !getenv("SIGOPS_NO_TMAP") && iir_tmap_available() &&
                 (rows % 32 == 0 || rows >= 256) && rows * 32 < (int64_t(1) << 31) && g.n_out < (int64_t(1) << 30)) {
                 const BufRef* refs = (const BufRef*)slot.last_table.data();
                 auto uniform = [&](int b, char*& base, int64_t& stride) {
                     const BufRef& r0 = refs[b];
                     base = (char*)r0.ptr;
-                    stride = r0.ld * 8;
-                    if ((stride & 15) || r0.dtype != SIGOPS_F64) return false;
+                    stride = r0.ld * esz;
+                    const int want = f32 ? SIGOPS_F32 : SIGOPS_F64;
+                    if ((stride & 15) || ((uintptr_t)base & 15) || r0.dtype != want) return false;
                     for (int64_t i = 0; i < ninst; ++i) {
                         const BufRef& rb = refs[i * nbuf + b];
-                        if (rb.ld != r0.ld || rb.nch != r0.nch || rb.dtype != SIGOPS_F64 ||
+                        if (rb.ld != r0.ld || rb.nch != r0.nch || rb.dtype != want ||
                             (char*)rb.ptr != base + (int64_t)i * r0.nch * stride)
                             return false;
                     }
@@ -872,22 +897,22 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                 };
                 char *bin = nullptr, *bout = nullptr;
                 int64_t sin_ = 0, sout = 0;
-                const int64_t Wst = round_up(std::max<int64_t>(s.iir.W, 1), kTmStageCols);
+                const int64_t Wst = round_up(std::max<int64_t>(s.iir.W, 1), stage_cols);
                 if (uniform(s.iir.plain_buf, bin, sin_) && uniform(g.out_buf, bout, sout) && 2 * Wst <= g.n_out) {
                     // chunk length: whole waves of one block (8 warps = 8 units) per SM; a unit walks L + Wc frames
                     const int64_t N = g.n_out, groups = (rows + 31) / 32;
                     const int nw = kTmWarps;
-                    const int64_t jmax = std::max<int64_t>(1, (N + kTmStageCols - 1) / kTmStageCols);
+                    const int64_t jmax = std::max<int64_t>(1, (N + stage_cols - 1) / stage_cols);
                     double best = 1e300;
                     int64_t bestL = 0;
-                    for (int64_t j = Wst / kTmStageCols + 1; j <= jmax; j += std::max<int64_t>(1, jmax / 4096)) {
-                        const int64_t L = j * kTmStageCols, cpr = (N + L - 1) / L;
+                    for (int64_t j = Wst / stage_cols + 1; j <= jmax; j += std::max<int64_t>(1, jmax / 4096)) {
+                        const int64_t L = j * stage_cols, cpr = (N + L - 1) / L;
                         const int64_t blocks = (groups * cpr + nw - 1) / nw;
                         const int64_t waves = (blocks + dev.sm_count - 1) / dev.sm_count;
                         const double cost = (double)waves * ((double)L + (cpr > 1 ? (double)Wst : 0.0) + 600.0);
                         if (cost < best) { best = cost; bestL = L; }
                     }
-                    if (const char* e = getenv("SIGOPS_IIR_L")) bestL = std::max<int64_t>(Wst + kTmStageCols, round_up(atoll(e), kTmStageCols));
+                    if (const char* e = getenv("SIGOPS_IIR_L")) bestL = std::max<int64_t>(Wst + stage_cols, round_up(atoll(e), stage_cols));
                     // A slowly decaying filter is better served by k_iir_tma's short chunks and carry pass.
                     // Both estimates are in lane-frames; a lane-frame takes about max(100, 0.82 * lanes per SM)
                     // cycles (measured: 210 with 256 lanes, 102 with 128), which makes them comparable.
@@ -895,8 +920,10 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                     const bool tmap_wins = best * frame_cycles(32 * nw) <=
                                            choose_iir_chunking_flat(s, rows, dev.sm_count).cost * frame_cycles(32 * kTmaWarps);
                     TensorMapBlob mi, mo;
-                    if (bestL > Wst && tmap_wins && iir_tmap_encode(&mi, bin, std::min<int64_t>(s.iir.plain_len, N), rows, sin_) &&
-                        iir_tmap_encode(&mo, bout, N, rows, sout)) {
+                    // (a Float32 stage has no other fast kernel to fall back on: take this one whenever it applies)
+                    if (bestL > Wst && (tmap_wins || f32) &&
+                        iir_tmap_encode(&mi, bin, std::min<int64_t>(s.iir.plain_len, N), rows, sin_, esz) &&
+                        iir_tmap_encode(&mo, bout, N, rows, sout, esz)) {
                         IirTmapParams T{};
                         T.bufrefs = d_refs; T.scalars = scalars; T.nbuf = nbuf; T.nscalars = nscal;
                         T.out_buf = g.out_buf; T.sumsq_slot = g.sumsq_slot; T.nch = g.nchannels; T.nrows = rows;
@@ -912,9 +939,9 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                         const bool unitb = s.iir.unitb;
                         dim3 tgrid((unsigned)((T.nunits + nw - 1) / nw));
                         if (getenv("SIGOPS_DEBUG"))
-                            fprintf(stderr, "[sigops] IIR stage %zu: tensor-map rows=%lld N=%lld M=%d W=%lld L=%lld chunks/row=%lld blocks=%u\n", si,
+                            fprintf(stderr, "[sigops] IIR stage %zu: tensor-map%s rows=%lld N=%lld M=%d W=%lld L=%lld chunks/row=%lld blocks=%u\n", si, f32 ? " (Float32)" : "",
                                     (long long)rows, (long long)N, M_, (long long)s.iir.W, (long long)T.L, (long long)T.cpr, tgrid.x);
-                        add(KIND_IIR_MAIN, [=](cudaStream_t st) { launch_iir_tmap(M_, unitb, tgrid, st, T, &mi, &mo); });
+                        add(KIND_IIR_MAIN, [=](cudaStream_t st) { launch_iir_tmap(f32, M_, unitb, tgrid, st, T, &mi, &mo); });
                         continue;
                     }
                 }

@@ -74,3 +74,20 @@ def test_slow_decay_batch_takes_short_chunks_and_the_carry_pass(gpu):
         want, _ = oracle.sink(chain(xs[k]))
         assert got[k][0].shape == want.shape
         assert np.max(np.abs(got[k][0] - want)) <= F64_TOL * rms(want)
+
+
+@pytest.mark.parametrize("ninst,nch,n", [(16, 2, 48000), (40, 2, 16032)])
+def test_float32_batch(gpu, ninst, nch, n):
+    """Float32 signals stay Float32 (runtests.jl:707-729); state and arithmetic are Float64."""
+    rng = np.random.default_rng(ninst + 1)
+    xs = [rng.standard_normal((n, nch)).astype(np.float32) for _ in range(ninst)]
+    chain = lambda x: Signal(x, 48 * kHz) >> Filt(Lowpass, 4 * kHz, order=8) >> Amplify(np.float32(-20) * dB)   # noqa: E731
+    a = run(gpu, [chain(x) for x in xs], tmap=True)
+    b = run(gpu, [chain(x) for x in xs], tmap=False)
+    for k in range(ninst):
+        assert a[k][0].dtype == np.float32 and a[k][0].shape == (n, nch)
+        assert np.max(np.abs(a[k][0].astype(np.float64) - b[k][0])) <= 2e-7 * rms(b[k][0]) + 1e-12
+    for k in (0, ninst - 1):
+        want, _ = oracle.sink(chain(xs[k]))
+        assert want.dtype == np.float32
+        assert np.max(np.abs(a[k][0].astype(np.float64) - want)) <= 1e-5 * rms(want)

@@ -1,5 +1,5 @@
 """Run a few device-resident steps of one BASELINE workload (for ncu / quick timing).
-usage: python tools/profile_step.py [cfg1|cfg2|cfg3|cfg4|cfg5] [steps] [ninst]"""
+usage: python tools/profile_step.py [cfg1|cfg2|cfg2f|cfg3|cfg4|cfg5] [steps] [ninst]"""
 import os
 import sys
 import time
@@ -29,6 +29,10 @@ if cfg == "cfg1":
 elif cfg == "cfg2":
     ninst = 256
     g = Signal(Z((480000, 2)), 48 * kHz) >> Filt(Lowpass, 4 * kHz, order=8) >> Amplify(-20 * dB)
+elif cfg == "cfg2f":      # config 2 on Float32 samples (half the bytes; state and arithmetic stay Float64)
+    ninst = 256
+    g = (Signal(np.zeros((480000, 2), dtype=np.float32), 48 * kHz) >> Filt(Lowpass, 4 * kHz, order=8)
+         >> Amplify(np.float32(-20) * dB))
 elif cfg == "cfg3":
     ninst = 64
     g = ToFramerate(Signal(Z((2646000, 2)), 44.1 * kHz), 48 * kHz)
@@ -54,15 +58,16 @@ ctx = cabi.Context([0])
 cp = cabi.CompiledPlan(ctx, plan.tobytes())
 gen = torch.Generator(device="cuda")
 gen.manual_seed(1983)
-xs = [torch.randn((ninst, d.nchannels, d.nframes), dtype=torch.float64, device="cuda", generator=gen) for d in plan.inputs]
-ys = [torch.empty((ninst, d.nchannels, d.nframes), dtype=torch.float64, device="cuda") for d in plan.outputs]
+tdt = lambda d: torch.float32 if d.dtype == cabi.F32 else torch.float64   # noqa: E731
+xs = [torch.randn((ninst, d.nchannels, d.nframes), dtype=tdt(d), device="cuda", generator=gen) for d in plan.inputs]
+ys = [torch.empty((ninst, d.nchannels, d.nframes), dtype=tdt(d), device="cuda") for d in plan.outputs]
 
 
 def bufs(ts):
     arr = (cabi.Buffer * (ninst * len(ts)))()
     for i in range(ninst):
         for k, t in enumerate(ts):
-            arr[i * len(ts) + k] = cabi.Buffer(t[i].data_ptr(), t.shape[2], t.shape[1], cabi.F64, t.shape[2])
+            arr[i * len(ts) + k] = cabi.Buffer(t[i].data_ptr(), t.shape[2], t.shape[1], cabi.F32 if t.dtype == torch.float32 else cabi.F64, t.shape[2])
     return arr
 
 
