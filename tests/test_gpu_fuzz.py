@@ -69,3 +69,47 @@ def test_random_batch_matches_oracle(gpu, seed):
         y, fs_got = got[k]
         assert fs_got == fs and y.shape == want.shape and y.dtype == want.dtype
         assert np.max(np.abs(y.astype(np.float64) - want.astype(np.float64))) <= tol * max(rms(want), 1e-300), (seed, k)
+
+
+def make_map_case(seed):
+    from signalops import AddChannel, After, Append, FadeTo, Mix, Ramp, ToChannels, cycle, mirror, ms, s, sin
+    r = np.random.default_rng(1000 + seed)
+    nch = int(r.choice([1, 2]))
+    ninst = int(r.choice([2, 40, 150]))
+    n = int(r.choice([3000, 20000, 44100]))
+    fs = float(r.choice([8000.0, 44100.0]))
+    dur = n / fs
+    kind = int(r.integers(0, 5))
+    w = float(r.uniform(50, 900))
+    if kind == 0:      # appended pieces with different programs, joint Normpower, gain
+        chain = lambda x: (Append(Signal(sin, ω=w * Hz) >> ToChannels(nch) >> Until(0.3 * s) >> Ramp(5 * ms), Signal(x, fs * Hz))   # noqa: E731
+                           >> Normpower >> Amplify(-12 * dB))
+    elif kind == 1:    # pads of every kind, cut in the padding
+        pad = [zero, cycle, mirror][int(r.integers(0, 3))]
+        chain = lambda x: Signal(x, fs * Hz) >> Pad(pad) >> Until((dur * 1.7) * s) >> Ramp(10 * ms) >> Normpower   # noqa: E731
+    elif kind == 2:    # mix with a generated tone, skip the head
+        chain = lambda x: Mix(Signal(x, fs * Hz), Signal(sin, ω=w * Hz, ϕ=0.25)) >> After(0.05 * s) >> Until((dur / 2) * s) >> Amplify(3 * dB)   # noqa: E731
+    elif kind == 3:    # cross-fade two data signals
+        chain = lambda x: FadeTo(Signal(x, fs * Hz), Signal(x[::-1].copy(), fs * Hz), 20 * ms)   # noqa: E731
+    else:              # channel plumbing + normalisation
+        chain = lambda x: Signal(x, fs * Hz) >> AddChannel(Signal(sin, ω=w * Hz) >> Until(dur * s)) >> Normpower >> Amplify(-20 * dB)   # noqa: E731
+    xs = [r.standard_normal((n, nch)) for _ in range(ninst)]
+    return xs, chain
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_random_map_batch_matches_oracle(gpu, seed):
+    xs, chain = make_map_case(seed)
+    saved = os.environ.pop("SIGOPS_HOST_WAVES", None)
+    try:
+        os.environ["SIGOPS_HOST_WAVES"] = "1"      # one wave: large launches take the multi-pass map kernel
+        got = sink_batch([chain(x) for x in xs], gpu)
+    finally:
+        os.environ.pop("SIGOPS_HOST_WAVES", None)
+        if saved is not None:
+            os.environ["SIGOPS_HOST_WAVES"] = saved
+    for k in sorted({0, len(xs) - 1}):
+        want, fs = oracle.sink(chain(xs[k]))
+        y, fs_got = got[k]
+        assert fs_got == fs and y.shape == want.shape
+        assert np.max(np.abs(y - want)) <= 1e-9 * max(rms(want), 1e-300), (seed, k)
