@@ -90,9 +90,10 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// MF = 8-row fragments per compute warp, RH = compute warps per output group (row slices):
+// MF = 8-row fragments per compute warp, RH = compute warps per output group (row slices), SSQ =
+// accumulate the sum of squares for a following Normpower (costs the compute warps 2*MF registers):
 // RB = 8*MF*RH rows per block, 4*RH compute warps followed by 4*RH aux warps.
-template <int MF, int RH>
+template <int MF, int RH, bool SSQ>
 __global__ void __launch_bounds__(8 * RH * 32, 1)
 k_fir_mma(const __grid_constant__ FirMmaParams P) {
     constexpr int RB = 8 * MF * RH;
@@ -299,11 +300,16 @@ k_fir_mma(const __grid_constant__ FirMmaParams P) {
         // ---------------- DMMA ----------------
         const int g = warp & 3, half = warp >> 2;
         const int kk = lane & 3, rr = lane >> 2;
-        double ssq[MF];
+        double ssq[SSQ ? MF : 1];
 #pragma unroll
-        for (int i = 0; i < MF; ++i) ssq[i] = 0.0;
+        for (int i = 0; i < (SSQ ? MF : 1); ++i) ssq[i] = 0.0;
+
         const int rbase = half * (RB / RH) + rr;          // my first row; fragment i holds row rbase + 8i
         const double* arow = ring + (size_t)rbase * P.pitch;
+        // output row pointers stay in registers: a store then depends on nothing but its fragment
+        double* dstp[MF];
+#pragma unroll
+        for (int i = 0; i < MF; ++i) dstp[i] = s_dst[rbase + 8 * i];
         int roff[MF];                                    // warp-uniform row offsets, kept out of the loop's address chain
 #pragma unroll
         for (int i = 0; i < MF; ++i) roff[i] = i * 8 * P.pitch;
@@ -314,14 +320,14 @@ k_fir_mma(const __grid_constant__ FirMmaParams P) {
         long long dbg_acc[4] = {0, 0, 0, 0};
         double prev[MF][2];                              // fragments of the previous tile, not yet stored
         int64_t mprev = -1;
+        bool prev_full = false;                          // both outputs of the pending fragments exist
         // fragment (outputs m, m+1 of one row) -> global; predicated, no branch on the row pointer
-        auto store_frag = [&](double* dst, int64_t m, double v0, double v1) {
-            if (dst && m + 1 < P.n_out) *reinterpret_cast<double2*>(dst + m) = make_double2(v0, v1);
+        auto store_frag = [&](double* dst, int64_t m, bool full, double v0, double v1) {
+            if (dst && full) *reinterpret_cast<double2*>(dst + m) = make_double2(v0, v1);
             else if (dst && m < P.n_out) dst[m] = v0;
         };
         // Sum of squares for a following Normpower: only when asked for, and as one batch per tile —
         // every switch of the FP64 pipe between DMMA and scalar FP64 work costs a pipeline drain.
-        const bool want_ssq = P.sumsq_slot >= 0;
         for (int64_t t = t0; t < t1; ++t) {
             const int s = (int)((t - t0) & 1);
             // first window position of my group, as a ring index
@@ -355,16 +361,17 @@ k_fir_mma(const __grid_constant__ FirMmaParams P) {
 #pragma unroll
             for (int i = 0; i < MF; ++i) {
                 if (i < nks) step(i);
-                if (mprev >= 0) store_frag(s_dst[rbase + 8 * i], mprev, prev[i][0], prev[i][1]);
+                if (mprev >= 0) store_frag(dstp[i], mprev, prev_full, prev[i][0], prev[i][1]);
             }
 #pragma unroll 2
             for (int ks = MF; ks < nks; ++ks) step(ks);
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_done[s]);
             mprev = t * kFmT + 8 * g + 2 * kk;
+            prev_full = mprev + 1 < P.n_out;
 #pragma unroll
             for (int i = 0; i < MF; ++i) { prev[i][0] = acc[i][0]; prev[i][1] = acc[i][1]; }
-            if (want_ssq) {
+            if (SSQ) {
                 // outputs past n_out have all-zero taps, so their fragments are exactly 0
 #pragma unroll
                 for (int i = 0; i < MF; ++i) ssq[i] = fma(acc[i][0], acc[i][0], fma(acc[i][1], acc[i][1], ssq[i]));
@@ -375,16 +382,16 @@ k_fir_mma(const __grid_constant__ FirMmaParams P) {
             }
         }
 #pragma unroll
-        for (int i = 0; i < MF; ++i) store_frag(s_dst[rbase + 8 * i], mprev, prev[i][0], prev[i][1]);
+        for (int i = 0; i < MF; ++i) store_frag(dstp[i], mprev, mprev + 1 < P.n_out, prev[i][0], prev[i][1]);
         if (P.dbg && warp == 0 && lane == 0)
             for (int i = 0; i < 4; ++i) P.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + 3 + i] = dbg_acc[i];
-        if (P.sumsq_slot >= 0) {
+        if (SSQ) {
 #pragma unroll
-            for (int i = 0; i < MF; ++i) {
+            for (int i = 0; i < (SSQ ? MF : 1); ++i) {
                 double v = ssq[i];
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
-                if (kk == 0 && s_dst[rbase + 8 * i]) atomicAdd(P.scalars + (size_t)s_inst[rbase + 8 * i] * P.nscalars + P.sumsq_slot, v);
+                if (kk == 0 && dstp[i]) atomicAdd(P.scalars + (size_t)s_inst[rbase + 8 * i] * P.nscalars + P.sumsq_slot, v);
             }
         }
     }

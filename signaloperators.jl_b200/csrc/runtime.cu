@@ -1104,11 +1104,11 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                         FirMmaParams D = Q;
                         D.dbg = dbg;
                         if (RB == 128 && RH == 2) {
-                            ensure_dyn_smem(k_fir_mma<8, 2>, smem);
-                            k_fir_mma<8, 2><<<grid, 16 * 32, smem, stream>>>(D);
+                            ensure_dyn_smem(k_fir_mma<8, 2, false>, smem);
+                            k_fir_mma<8, 2, false><<<grid, 16 * 32, smem, stream>>>(D);
                         } else if (RB == 128) {
-                            ensure_dyn_smem(k_fir_mma<16, 1>, smem);
-                            k_fir_mma<16, 1><<<grid, 8 * 32, smem, stream>>>(D);
+                            ensure_dyn_smem(k_fir_mma<16, 1, false>, smem);
+                            k_fir_mma<16, 1, false><<<grid, 8 * 32, smem, stream>>>(D);
                         }
                         CUDA_OK(cudaStreamSynchronize(stream));
                         std::vector<long long> h(nb * 8);
@@ -1124,8 +1124,13 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                     add(KIND_FIR, [=](cudaStream_t st) {
 #define SIGOPS_FIR_MMA_CASE(rb, rh)                                                          \
     if (RB == rb && RH == rh) {                                                              \
-        ensure_dyn_smem(k_fir_mma<rb / (8 * rh), rh>, smem);                                 \
-        k_fir_mma<rb / (8 * rh), rh><<<grid, 8 * rh * 32, smem, st>>>(Q);                   \
+        if (Q.sumsq_slot >= 0) {                                                             \
+            ensure_dyn_smem(k_fir_mma<rb / (8 * rh), rh, true>, smem);                       \
+            k_fir_mma<rb / (8 * rh), rh, true><<<grid, 8 * rh * 32, smem, st>>>(Q);         \
+        } else {                                                                             \
+            ensure_dyn_smem(k_fir_mma<rb / (8 * rh), rh, false>, smem);                      \
+            k_fir_mma<rb / (8 * rh), rh, false><<<grid, 8 * rh * 32, smem, st>>>(Q);        \
+        }                                                                                    \
     }
                         SIGOPS_FIR_MMA_CASE(128, 1) SIGOPS_FIR_MMA_CASE(64, 1) SIGOPS_FIR_MMA_CASE(32, 1)
                         SIGOPS_FIR_MMA_CASE(128, 2) SIGOPS_FIR_MMA_CASE(64, 2) SIGOPS_FIR_MMA_CASE(32, 2)
