@@ -323,7 +323,7 @@ k_fir_mma(const __grid_constant__ FirMmaParams P) {
         bool prev_full = false;                          // both outputs of the pending fragments exist
         // fragment (outputs m, m+1 of one row) -> global; predicated, no branch on the row pointer
         auto store_frag = [&](double* dst, int64_t m, bool full, double v0, double v1) {
-            if (dst && full) *reinterpret_cast<double2*>(dst + m) = make_double2(v0, v1);
+            if (dst && full) __stcs(reinterpret_cast<double2*>(dst + m), make_double2(v0, v1));   // streaming: never re-read
             else if (dst && m < P.n_out) dst[m] = v0;
         };
         // Sum of squares for a following Normpower: only when asked for, and as one batch per tile —
