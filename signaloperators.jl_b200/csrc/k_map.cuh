@@ -79,7 +79,7 @@ k_map(const __grid_constant__ MapParams P) {
 #pragma unroll
             for (int j = 0; j < kMapV; ++j)
                 if (n0 + (int64_t)j * kMapThreads < nend) {
-                    __stcs(op + j * kMapThreads, acc[j]);       // batches stream: nothing here is re-read from L2
+                    op[j * kMapThreads] = acc[j];
                     ss = fma(acc[j], acc[j], ss);
                 }
         } else {
