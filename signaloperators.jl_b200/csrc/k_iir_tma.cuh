@@ -5,16 +5,16 @@
 // in, Float64 buffer out, constant-gain epilogue, 16-byte aligned channels.
 //
 // Every lane is an independent stream: lane = one chunk of one channel.  The chunk
-// moves through two private 64-frame shared-memory stages:
-//     cp.async.bulk global -> shared (512 B, mbarrier complete_tx)        [TMA load]
+// moves through two private 48-frame shared-memory stages:
+//     cp.async.bulk global -> shared (384 B, mbarrier complete_tx)        [TMA load]
 //     cascade in place on the stage (register-blocked, software-pipelined)
-//     cp.async.bulk shared -> global (512 B, bulk_group)                   [TMA store]
+//     cp.async.bulk shared -> global (384 B, bulk_group)                   [TMA store]
 // When the cascade's zero-input response dies out within Wc < L frames the kernel runs
 // in WARM mode instead: chunk k >= 1 starts Wc frames early from zero state and simply
 // discards those outputs — after Wc frames its state equals the sequential filter's to
 // 2^-64 of full scale — so one launch produces final results and no CARRY/FIX pass,
 // state array or second trip over the data is needed.
-// Each global access is a contiguous 512-byte segment, no thread ever waits on
+// Each global access is a contiguous 384-byte segment, no thread ever waits on
 // another lane's data, and while a stage is being filtered the next one is already in
 // flight.  Chunks are numbered over (instance, channel, chunk) jointly, so a warp's 32
 // lanes may belong to different channels and the grid can be sized to whole waves.
@@ -177,7 +177,7 @@ k_iir_tma(const __grid_constant__ IirTmaParams Q) {
         if (!active) src_len = 0;
     }
     const double* gsrc = (MODE == IIR_FIX) ? yout : xin - pre;
-    double* const gdst = yout - pre;                          // stage h of the lane lands at gdst + h*64
+    double* const gdst = yout - pre;                          // stage h of the lane lands at gdst + h*kStageCols
     const int64_t nstage = (work + kStageCols - 1) / kStageCols;
 
     mbar_init(&bars[0], 1);
@@ -204,7 +204,7 @@ k_iir_tma(const __grid_constant__ IirTmaParams Q) {
     double ss = 0.0;
     unsigned parity = 0u, pending = 0u;      // bit b: mbarrier phase / TMA load in flight for stage b
 
-    // Stage h of my chunk -> shared.  Full 64-frame stages go through the TMA; a ragged
+    // Stage h of my chunk -> shared.  Full stages go through the TMA; a ragged
     // last stage (or input shorter than the output: zero padding) is copied by the lane.
     auto issue_load = [&](int64_t h) {
         const unsigned b = (unsigned)(h & 1);
