@@ -44,11 +44,13 @@ constexpr int kTmSub = 16;                       // Float64 frames per 128-byte 
 #endif
 // 80-frame stages: 640 contiguous bytes per row and copy.  An odd number of blocks per row also keeps
 // the swizzle key (blocks*row + block) mod 8 different for 8 consecutive rows (4 blocks: 4-way conflicts).
-constexpr int kTmSubsPerStage = TMSUBS;
+constexpr int kTmSubsPerStage = TMSUBS;                  // Float64 shape
 constexpr int kTmStageCols = kTmSub * kTmSubsPerStage;   // Float64 frames per stage
-constexpr int kTmSubBytes = 32 * kTmSub * 8;     // 4096
-constexpr int kTmStageBytes = kTmSubBytes * kTmSubsPerStage;
-constexpr size_t tm_smem_bytes(int nw, int ns) { return (size_t)nw * ns * kTmStageBytes + 1024; }   // + slack to align to 1024
+constexpr int kTmSubBytes = 32 * 128;                    // one box row block: 32 rows x 128 bytes
+// Float32 shape: the bytes per sample halve while the FP64 work per sample stays, so the kernel is
+// bound by its dependency chains — twice the warps, 3-block stages (96 frames, 384 bytes per row)
+constexpr int kTmSubsPerStageF32 = 3, kTmWarpsF32 = 8;
+constexpr size_t tm_smem_bytes(int nw, int ns, int subs) { return (size_t)nw * ns * subs * kTmSubBytes + 1024; }   // + 1024-byte alignment slack
 
 struct IirTmapParams {
     const BufRef* bufrefs;
@@ -129,20 +131,22 @@ __device__ __forceinline__ double cascade16_swz(Cascade<M>& f, unsigned char* ro
     return ss;
 }
 
-// NW warps per block, NS stages per warp (NS - 1 loads in flight while one stage is filtered).
-template <int M, bool UNITB, int NW, int NS, class T>
+// NW warps per block, NS stages per warp (NS - 1 loads in flight while one stage is filtered), SUBS
+// 128-byte blocks per row and stage (odd: keeps the swizzle key distinct for 8 consecutive rows).
+template <int M, bool UNITB, int NW, int NS, int SUBS, class T>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUtensorMap tm_in,
            const __grid_constant__ CUtensorMap tm_out) {
     constexpr int SUB = 128 / (int)sizeof(T);        // frames per 128-byte box row: 16 or 32
-    constexpr int SC = SUB * kTmSubsPerStage;        // frames per stage: 80 or 160
+    constexpr int SC = SUB * SUBS;                   // frames per stage
+    constexpr int kStageB = SUBS * kTmSubBytes;      // bytes per stage
     extern __shared__ unsigned char tm_smem_raw[];
     __shared__ uint64_t bars[NW][NS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // 1024-byte aligned stage buffers (the swizzle pattern is a function of address bits 4-9)
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tm_smem_raw) + 1023) & ~uintptr_t(1023));
-    unsigned char* const stage0 = base + (size_t)warp * NS * kTmStageBytes;
-    auto stage_of = [&](int b) { return stage0 + b * kTmStageBytes; };
+    unsigned char* const stage0 = base + (size_t)warp * NS * kStageB;
+    auto stage_of = [&](int b) { return stage0 + b * kStageB; };
 
     const int64_t unit = (int64_t)blockIdx.x * NW + warp;             // (row group, chunk)
     if (unit >= P.nunits) return;
@@ -180,7 +184,7 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
     auto issue_load = [&](int64_t h) {
         if (lane == 0) {
             const int b = (int)(h % NS);
-            mbar_expect_tx(&bars[warp][b], kTmStageBytes);
+            mbar_expect_tx(&bars[warp][b], kStageB);
             tmap_load_3d(stage_of(b), &tm_in, 0, (int)((start + h * SC) / SUB), c1, &bars[warp][b]);
         }
     };
@@ -195,15 +199,15 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
         const int64_t off = h * SC;
         // smem box layout: [row][block][128 bytes]; the 128-byte swizzle XORs the 16-byte chunk index
         // with address bits 7-9 = (blocks_per_stage*row + block) mod 8
-        unsigned char* rowp = stage_of(b) + lane * (kTmSubsPerStage * 128);
+        unsigned char* rowp = stage_of(b) + lane * (SUBS * 128);
         const bool keep = off >= pre;                                  // pre is a multiple of the stage
         double s3 = 0.0;
 #pragma unroll
-        for (int s = 0; s < kTmSubsPerStage; ++s) {
+        for (int s = 0; s < SUBS; ++s) {
 #pragma unroll
             for (int blk = 0; blk < SUB / 16; ++blk) {
                 const int64_t rem = work - off - s * SUB - blk * 16;   // outputs of this block that exist
-                s3 += cascade16_swz<M, UNITB, T>(f, rowp + s * 128, (kTmSubsPerStage * lane + s) & 7, blk, P.gain, P.scale,
+                s3 += cascade16_swz<M, UNITB, T>(f, rowp + s * 128, (SUBS * lane + s) & 7, blk, P.gain, P.scale,
                                                  rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0));
             }
             if (s == 0 && h + NS - 1 < nstage) {

@@ -877,7 +877,7 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
             // within a chunk (WARM).
             const bool f32 = s.iir.fast32;
             const int esz = f32 ? 4 : 8;
-            const int stage_cols = kTmStageCols * (f32 ? 2 : 1);
+            const int stage_cols = f32 ? 32 * kTmSubsPerStageF32 : kTmStageCols;
             if (((tma && s.iir.fast && !s.iir.tma_prog) || f32) && !getenv("SIGOPS_NO_TMAP") && iir_tmap_available() &&
                 (rows % 32 == 0 || rows >= 256) && rows * 32 < (int64_t(1) << 31) && g.n_out < (int64_t(1) << 30)) {
                 const BufRef* refs = (const BufRef*)slot.last_table.data();
@@ -901,7 +901,7 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                 if (uniform(s.iir.plain_buf, bin, sin_) && uniform(g.out_buf, bout, sout) && 2 * Wst <= g.n_out) {
                     // chunk length: whole waves of one block (8 warps = 8 units) per SM; a unit walks L + Wc frames
                     const int64_t N = g.n_out, groups = (rows + 31) / 32;
-                    const int nw = kTmWarps;
+                    const int nw = f32 ? kTmWarpsF32 : kTmWarps;
                     const int64_t jmax = std::max<int64_t>(1, (N + stage_cols - 1) / stage_cols);
                     double best = 1e300;
                     int64_t bestL = 0;
