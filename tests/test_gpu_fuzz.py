@@ -50,7 +50,7 @@ def make_case(seed):
     return xs, (lambda x: tail(Signal(x, fs * Hz))), f32
 
 
-@pytest.mark.parametrize("seed", range(60))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("SIGOPS_FUZZ_SEEDS", "60"))))
 def test_random_batch_matches_oracle(gpu, seed):
     xs, chain, f32 = make_case(seed)
     # every other case runs the batch as ONE wave, so that the many-row kernels see it whole
@@ -97,7 +97,7 @@ def make_map_case(seed):
     return xs, chain
 
 
-@pytest.mark.parametrize("seed", range(20))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("SIGOPS_FUZZ_MAP_SEEDS", "20"))))
 def test_random_map_batch_matches_oracle(gpu, seed):
     xs, chain = make_map_case(seed)
     saved = os.environ.pop("SIGOPS_HOST_WAVES", None)
