@@ -222,6 +222,12 @@ __device__ __forceinline__ void buf_values(const sigops_instr& I, const sigops_i
         for (int j = 0; j < V; ++j) out[j] = __ldg(p + j * nstride);
         return;
     }
+    if (b.dtype == SIGOPS_F32 && idx0 >= 0 && idx0 + (V - 1) * nstride < I.i1) {
+        const float* p = reinterpret_cast<const float*>(b.ptr) + (int64_t)ch * b.ld + idx0;
+#pragma unroll
+        for (int j = 0; j < V; ++j) out[j] = (double)__ldg(p + j * nstride);
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < V; ++j) out[j] = leaf_value_slow(Ip, env.bufs, n0 + j * nstride, c);
 }

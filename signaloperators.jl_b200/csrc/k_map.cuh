@@ -82,6 +82,15 @@ k_map(const __grid_constant__ MapParams P) {
                     op[j * kMapThreads] = acc[j];
                     ss = fma(acc[j], acc[j], ss);
                 }
+        } else if (ob.dtype == SIGOPS_F32) {
+            float* op = reinterpret_cast<float*>(ob.ptr) + (int64_t)c * ob.ld + n0;
+#pragma unroll
+            for (int j = 0; j < kMapV; ++j)
+                if (n0 + (int64_t)j * kMapThreads < nend) {
+                    const float v = (float)acc[j];
+                    op[j * kMapThreads] = v;
+                    ss = fma((double)v, (double)v, ss);
+                }
         } else {
 #pragma unroll
             for (int j = 0; j < kMapV; ++j) {

@@ -573,12 +573,17 @@ class Lowerer:
         else:
             n_in = cn
         prog, plain = self._input_program(child, n_in, C)
-        if not plain:
-            tag_in = self.add_temp(n_in, C, child.sampletype)
+        # The tensor-core kernel (csrc/k_fir_mma.cuh) wants plain Float64 rows on both sides.  Float32
+        # signals are widened once on the way in and rounded once on the way out — the rounding the
+        # reference's Float32 output block performs (src/filters.jl:213-214) — which costs two light
+        # elementwise passes and still beats the scalar kernel by a wide margin.
+        f32 = np.dtype(T) == np.float32
+        if not plain or np.dtype(child.sampletype) == np.float32:
+            tag_in = self.add_temp(n_in, C, np.float64 if np.dtype(child.sampletype) == np.float32 else child.sampletype)
             self.plan.stages.append(Stage(STAGE_MAP, tag_in, nchannels=C, n_out=n_in,
                                           pieces=[Piece(0, n_in, 0, C, prog)]))
             prog = [Instr(OP_LOAD, LEAF_BUF, buf=tag_in, i0=0, i1=n_in, d0=0.0)]
-        tag = self.add_temp(n_out, C, T)
+        tag = self.add_temp(n_out, C, np.float64 if f32 else T)
         st = Stage(STAGE_FIR, tag, in_prog=prog, nchannels=C, n_in=n_in, n_out=n_out,
                    rate=float(f.rate), input_deficit=int(f.input_deficit))
         if f.kind == "arbitrary":
@@ -602,6 +607,11 @@ class Lowerer:
         else:
             raise LoweringError("single-rate FIR filters are not lowered to the GPU path yet")
         self.plan.stages.append(st)
+        if f32:
+            tag32 = self.add_temp(n_out, C, T)
+            self.plan.stages.append(Stage(STAGE_MAP, tag32, nchannels=C, n_out=n_out, pieces=[Piece(
+                0, n_out, 0, C, [Instr(OP_LOAD, LEAF_BUF, buf=tag, i0=0, i1=n_out, d0=0.0), Instr(op=OP_CAST_F32)])]))
+            return tag32
         return tag
 
     # ---- maps ---------------------------------------------------------------------------
@@ -699,7 +709,17 @@ class Lowerer:
                 cands = {I.buf for I in refs}
                 for tag in cands:
                     prod = next((s for s in self.plan.stages[:i] if s.out_buf == tag), None)
-                    if prod is None or prod.kind == STAGE_MAP or prod.epi_prog or prod.sumsq_slot >= 0:
+                    if prod is None or prod.epi_prog or prod.sumsq_slot >= 0:
+                        continue
+                    bare_copy = (len(pc.prog) == 1 and pc.prog[0].op == OP_LOAD and
+                                 self._desc(st.out_buf).dtype == self._desc(tag).dtype)
+                    # an elementwise producer only absorbs a bare copy of its whole output (it then
+                    # writes straight into the copy's destination)
+                    if prod.kind == STAGE_MAP and not bare_copy:
+                        continue
+                    # resamplers keep a bare store: that is what the tensor-core kernel takes, and a
+                    # separate elementwise pass over its output costs far less than the scalar FIR kernel
+                    if prod.kind == STAGE_FIR and not bare_copy:
                         continue
                     uses = [I for I in refs if I.buf == tag]
                     elsewhere = any(I.leaf in (LEAF_BUF, LEAF_CHANSUM) and I.buf == tag
@@ -716,6 +736,12 @@ class Lowerer:
                     ob = self._desc(obuf)
                     if ob.nframes != prod.n_out or ob.nchannels != prod.nchannels:
                         continue
+                    if prod.kind == STAGE_MAP:
+                        prod.out_buf = obuf
+                        prod.sumsq_slot = st.sumsq_slot
+                        self.plan.stages.pop(i)
+                        changed = True
+                        break
                     prod.epi_prog = [replace(I, leaf=LEAF_STAGE, buf=0) if I is I0 else I for I in pc.prog]
                     prod.out_buf = obuf
                     prod.sumsq_slot = st.sumsq_slot

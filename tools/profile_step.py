@@ -1,5 +1,5 @@
 """Run a few device-resident steps of one BASELINE workload (for ncu / quick timing).
-usage: python tools/profile_step.py [cfg1|cfg2|cfg2f|cfg3|cfg4|cfg5] [steps] [ninst]"""
+usage: python tools/profile_step.py [cfg1|cfg2|cfg2f|cfg3|cfg3f|cfg3a|cfg4|cfg5] [steps] [ninst]"""
 import os
 import sys
 import time
@@ -36,6 +36,12 @@ elif cfg == "cfg2f":      # config 2 on Float32 samples (half the bytes; state a
 elif cfg == "cfg3":
     ninst = 64
     g = ToFramerate(Signal(Z((2646000, 2)), 44.1 * kHz), 48 * kHz)
+elif cfg == "cfg3f":      # config 3 on Float32 samples: widen, tensor-core FIR, round
+    ninst = 64
+    g = ToFramerate(Signal(np.zeros((2646000, 2), dtype=np.float32), 44.1 * kHz), 48 * kHz)
+elif cfg == "cfg3a":      # config 3 followed by a gain: FIR kernel + one elementwise pass
+    ninst = 64
+    g = ToFramerate(Signal(Z((2646000, 2)), 44.1 * kHz), 48 * kHz) >> Amplify(-6 * dB)
 elif cfg == "cfg4":
     ninst = 512
     fs = 44.1 * kHz
