@@ -274,6 +274,16 @@ def test_float32_stays_float32(gpu):
     assert got.dtype == np.float32
 
 
+def test_float32_resample(gpu):
+    """Float32 data through ToFramerate: widened for the FIR stage, rounded after it, Float32 out."""
+    x = rng(5).standard_normal((3000, 2)).astype(np.float32)
+    for mk in (lambda: ToFramerate(Signal(x, 8 * kHz), 11.025 * kHz),
+               lambda: ToFramerate(Signal(x, 8 * kHz), 4 * kHz) >> Amplify(np.float32(-6) * dB),
+               lambda: ToFramerate(Signal(x, 8 * kHz), 12 * kHz) >> Normpower):
+        got = check(gpu, mk, tol=F32_TOL)
+        assert got.dtype == np.float32
+
+
 # ---- batches -----------------------------------------------------------------------------------------------------
 
 def test_batch_matches_single(gpu):
