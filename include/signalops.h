@@ -240,7 +240,7 @@ typedef struct sigops_stage {
     int64_t input_deficit;           /* kernel.inputDeficit after setphase! (1-based)    */
     double  rate;                    /* FIRArbitrary.rate                                */
     double  phase0;                  /* phiAccumulator (arbitrary) or phiIdx (rational)  */
-} sigops_stage;            /* 136 bytes */
+} sigops_stage;            /* 128 bytes */
 
 #ifdef __cplusplus
 }

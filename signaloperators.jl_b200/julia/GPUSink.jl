@@ -154,8 +154,129 @@ struct Plan
     inputs::Vector{Array}
 end
 
+# ---- plan bytes (include/signalops.h; field order as in host/lowering.py `Plan.tobytes`) ----------------
+const MAGIC = 0x504F4753; const PLAN_VERSION = UInt32(1)
+const OP_LOAD, OP_MUL, OP_CAST_F32 = UInt8(1), UInt8(4), UInt8(12)
+const LEAF_NONE, LEAF_CONST, LEAF_BUF, LEAF_STAGE = UInt8(0), UInt8(1), UInt8(2), UInt8(8)
+const STAGE_IIR, STAGE_FIR = Int32(2), Int32(3)
+const FIR_ARBITRARY, FIR_RATIONAL, FIR_DECIMATOR = Int32(1), Int32(2), Int32(3)
+
+struct Instr                      # sigops_instr, 80 bytes
+    op::UInt8; leaf::UInt8; fn::UInt8; flags::UInt8
+    buf::Int32; c_mul::Int32; c_off::Int32
+    i0::Int64; i1::Int64; i2::Int64
+    d0::Float64; d1::Float64; d2::Float64; d3::Float64; d4::Float64
+end
+Instr(op, leaf; buf = 0, i1 = 0, d0 = 0.0) =
+    Instr(op, leaf, 0x00, 0x00, Int32(buf), Int32(1), Int32(0), 0, Int64(i1), 0, Float64(d0), 0.0, 0.0, 0.0, 0.0)
+put(io, x::Instr) = foreach(f -> write(io, htol(getfield(x, f))), fieldnames(Instr))
+
+Base.@kwdef struct Stage          # sigops_stage, 128 bytes
+    kind::Int32; out_buf::Int32; sumsq_slot::Int32 = -1
+    piece_start::Int32 = 0; n_pieces::Int32 = 0
+    in_prog_start::Int32; in_prog_len::Int32; epi_prog_start::Int32; epi_prog_len::Int32
+    nchannels::Int32; n_in::Int64; n_out::Int64
+    n_sections::Int32 = 0; coef_table::Int32 = -1; gain::Float64 = 1.0
+    fir_kind::Int32 = 0; n_phases::Int32 = 0; taps_per_phase::Int32 = 0
+    pfb_table::Int32 = -1; dpfb_table::Int32 = -1; interpolation::Int32 = 0; decimation::Int32 = 0
+    reserved0::Int32 = 0; input_deficit::Int64 = 0; rate::Float64 = 0.0; phase0::Float64 = 0.0
+end
+put(io, x::Stage) = foreach(f -> write(io, htol(getfield(x, f))), fieldnames(Stage))
+
+function planbytes(bufs, tables::Vector{Vector{Float64}}, instrs::Vector{Instr}, stages::Vector{Stage},
+                   n_inputs, n_temps, n_outputs)
+    io = IOBuffer()
+    blob = reduce(vcat, tables; init = Float64[])
+    foreach(v -> write(io, htol(UInt32(v))),
+            (MAGIC, PLAN_VERSION, n_inputs, n_temps, n_outputs, 0, length(tables), length(instrs), 0, length(stages)))
+    write(io, htol(UInt64(length(blob))))
+    for (n, c, dt) in bufs                       # sigops_bufdesc: inputs, temps, outputs
+        write(io, htol(Int64(n))); write(io, htol(Int32(c))); write(io, htol(Int32(dt)))
+    end
+    off = 0
+    for tb in tables                             # sigops_tabledesc
+        write(io, htol(Int64(off))); write(io, htol(Int64(length(tb)))); off += length(tb)
+    end
+    foreach(i -> put(io, i), instrs)
+    foreach(s -> put(io, s), stages)             # (no MAP stages here, hence no pieces)
+    foreach(v -> write(io, htol(v)), blob)
+    take!(io)
+end
+
+# ---- lowering ---------------------------------------------------------------------------------------------
+# Implemented here for the two barrier shapes of the benchmark configurations — the ones whose whole
+# cost is a kernel of this library:
+#     (array, fs) |> Filt(...) [|> Amplify(number)]...        one STAGE_IIR with a gain epilogue
+#     ToFramerate((array, fs), fs2)                            one STAGE_FIR
+# Every other graph needs the general recursion of host/lowering.py (`Lowerer.lower`, ~700 lines of
+# Python that this function should be a transcription of); it is reported as such rather than guessed at.
+# UNTESTED: written against src/filters.jl:96-107, src/mapsignal.jl:8-17,131-145,183-186,
+# src/numbers.jl:1-4, src/reformatting.jl:92-122 and SURVEY.md App. B without a Julia toolchain.
+isarraysignal(x) = x isa Tuple{<:AbstractArray,<:Number}
+
 function lower(x; nframes = SignalOperators.nframes(x), eltype = sampletype(x))
-    error("GPUSinks.lower: see host/lowering.py — port pending a Julia toolchain to test it against")
+    # peel `Amplify(number)` layers: MapSignal(FnBr(*), ...) over (signal, NumberSignal...)  (src/mapsignal.jl:131-145)
+    gains = Float64[]
+    r = x
+    while r isa MapSignal && r.fn isa FnBr && r.fn.fn === (*) && r.bychannel &&
+          all(s -> s isa NumberSignal, Base.tail(r.signals))
+        prepend!(gains, Float64[s.val for s in Base.tail(r.signals)])   # NumberSignal.val is already 10^(dB/20)
+        r = first(r.signals)
+    end
+    (r isa FilteredSignal && isarraysignal(r.signal) && length(gains) <= 2) ||
+        error("GPUSinks.lower: only `array |> Filt |> Amplify(number)` and `ToFramerate(array)` are transcribed ",
+              "to Julia so far; see host/lowering.py for the general lowering of ", typeof(x))
+    data = r.signal[1] isa AbstractVector ? reshape(r.signal[1], :, 1) : r.signal[1]
+    T = Base.eltype(data)
+    (T === Float64 || T === Float32) || error("GPUSinks.lower: sample type $T")
+    nin, C = size(data)
+    dt = dtypecode(T)
+    h = r.fn(framerate(r))                                   # design at sink time, src/filters.jl:205
+    load = Instr(OP_LOAD, LEAF_BUF; buf = 0, i1 = nin)       # zero padded past the input, src/filters.jl:240
+    epi = Instr[Instr(OP_LOAD, LEAF_STAGE)]
+    foreach(g -> push!(epi, Instr(OP_MUL, LEAF_CONST; d0 = g)), gains)
+    T === Float32 && !isempty(gains) && push!(epi, Instr(OP_CAST_F32, LEAF_NONE))
+    length(epi) == 1 && empty!(epi)
+    if h isa DSP.Filters.FIRFilter                           # resampler, src/reformatting.jl:92-99
+        isempty(gains) || error("GPUSinks.lower: gains after ToFramerate need the general lowering (separate MAP stage)")
+        T === Float64 || error("GPUSinks.lower: Float32 resampling needs the widen/round stages of host/lowering.py")
+        k = h.kernel
+        common = (kind = STAGE_FIR, out_buf = Int32(1), in_prog_start = Int32(0), in_prog_len = Int32(1),
+                  epi_prog_start = Int32(1), epi_prog_len = Int32(0), nchannels = Int32(C), n_in = nin, n_out = nframes,
+                  input_deficit = Int64(k.inputDeficit))
+        if k isa DSP.Filters.FIRArbitrary
+            tables = [vec(collect(Float64, k.pfb)), vec(collect(Float64, k.dpfb))]      # column phi = [phase][tap]
+            st = Stage(; common..., fir_kind = FIR_ARBITRARY, n_phases = Int32(k.Nϕ), taps_per_phase = Int32(k.tapsPerϕ),
+                       pfb_table = Int32(0), dpfb_table = Int32(1), rate = Float64(k.rate), phase0 = Float64(k.ϕAccumulator))
+        elseif k isa DSP.Filters.FIRRational || k isa DSP.Filters.FIRInterpolator
+            tables = [vec(collect(Float64, k.pfb))]
+            q = k isa DSP.Filters.FIRRational ? denominator(k.ratio) : 1
+            st = Stage(; common..., fir_kind = FIR_RATIONAL, n_phases = Int32(k.Nϕ), taps_per_phase = Int32(k.tapsPerϕ),
+                       pfb_table = Int32(0), interpolation = Int32(k.Nϕ), decimation = Int32(q), phase0 = Float64(k.ϕIdx))
+        elseif k isa DSP.Filters.FIRDecimator
+            tables = [collect(Float64, k.h)]                 # stored reversed by DSP.jl: window order
+            st = Stage(; common..., fir_kind = FIR_DECIMATOR, n_phases = Int32(1), taps_per_phase = Int32(k.hLen),
+                       pfb_table = Int32(0), interpolation = Int32(1), decimation = Int32(k.decimation), phase0 = 1.0)
+        else
+            error("GPUSinks.lower: single-rate FIR kernels are not lowered")
+        end
+        instrs = Instr[load]
+    else                                                     # IIR: DF2T second-order sections, SURVEY.md App. B.2
+        sos = convert(DSP.SecondOrderSections, h)
+        M = length(sos.biquads)
+        M <= 8 || error("GPUSinks.lower: cascades of more than 8 sections are split by host/lowering.py")
+        coef = Float64[]
+        for b in sos.biquads
+            append!(coef, (b.b0, b.b1, b.b2, b.a1, b.a2))
+        end
+        tables = [coef]
+        instrs = vcat(Instr[load], epi)
+        st = Stage(kind = STAGE_IIR, out_buf = Int32(1), in_prog_start = Int32(0), in_prog_len = Int32(1),
+                   epi_prog_start = Int32(1), epi_prog_len = Int32(length(epi)), nchannels = Int32(C), n_in = nframes,
+                   n_out = nframes, n_sections = Int32(M), coef_table = Int32(0), gain = Float64(sos.g))
+    end
+    bufs = [(nin, C, dt), (nframes, C, dtypecode(eltype))]
+    Plan(planbytes(bufs, tables, instrs, [st], 1, 0, 1), Array[data])
 end
 
 end # module
