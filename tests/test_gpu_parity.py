@@ -274,6 +274,30 @@ def test_float32_stays_float32(gpu):
     assert got.dtype == np.float32
 
 
+def test_more_reference_sets(gpu):
+    """Chains of runtests.jl:103-114 (channel counts), 461-470 (automatic reformatting),
+    481-488 / 550-575 (empty and cut infinite signals), 602-614 (frame units)."""
+    tone = lambda: Signal(sin, 22 * Hz, ω=10 * Hz) >> Until(5 * s)   # noqa: E731
+    data = check(gpu, lambda: tone() >> ToChannels(2), tol=1e-10)
+    check(gpu, lambda: Signal(data, 22 * Hz) >> ToChannels(1), exact=True)
+    a = lambda: Signal(sin, 200 * Hz, ω=10 * Hz) >> ToChannels(2) >> Until(5 * s)   # noqa: E731
+    b = lambda: Signal(sin, 100 * Hz, ω=5 * Hz) >> Until(3 * s)                     # noqa: E731
+    assert check(gpu, lambda: Mix(a(), b()), tol=1e-10).shape == (1000, 2)
+    assert check(gpu, lambda: Mix(a(), b(), 1), tol=1e-10).shape == (1000, 2)
+    for nch in (1, 2):
+        t0 = lambda: Signal(sin, 200 * Hz, ω=10 * Hz) >> ToChannels(nch)   # noqa: E731
+        assert check(gpu, lambda: t0() >> Until(10 * frames) >> Until(0 * frames)).shape == (0, nch)
+        assert check(gpu, lambda: t0() >> Until(10 * frames) >> After(5 * frames) >> After(2 * frames), tol=1e-10).shape == (3, nch)
+        assert check(gpu, lambda: t0() >> After(5 * frames) >> Until(5 * frames), tol=1e-10)[0, 0] > 0.9
+    x, y = rng(3).random((100, 2)), rng(4).random((50, 2))
+    X, Y = (lambda: Signal(x, 10 * Hz)), (lambda: Signal(y, 10 * Hz))
+    for mk, n in ((lambda: X() >> Until(30 * frames), 30), (lambda: X() >> After(30 * frames), 70),
+                  (lambda: X() >> Append(Y()) >> After(20 * frames), 130), (lambda: X() >> Append(Y()) >> Until(130 * frames), 130),
+                  (lambda: X() >> Pad(zero) >> Until(150 * frames), 150), (lambda: X() >> Ramp(10 * frames), 100)):
+        assert check(gpu, mk).shape[0] == n
+    assert check(gpu, lambda: X() >> FadeTo(Y(), 10 * frames)).shape[0] > 100
+
+
 def test_float32_resample(gpu):
     """Float32 data through ToFramerate: widened for the FIR stage, rounded after it, Float32 out."""
     x = rng(5).standard_normal((3000, 2)).astype(np.float32)

@@ -302,3 +302,55 @@ def test_unknown_frame_rates():                                  # runtests.jl:7
         assert arr(g >> ToFramerate(10 * Hz)).shape[0] == n
     with pytest.raises(SignalError):
         oracle.sink(FadeTo(x, y) >> ToFramerate(10 * Hz))
+
+
+def test_change_channel_count():                                  # runtests.jl:103-114
+    tone = Signal(sin, 22 * Hz, ω=10 * Hz) >> Until(5 * s)
+    assert nchannels(tone >> ToChannels(2)) == 2 and nchannels(tone >> ToChannels(1)) == 1
+    data = arr(tone >> ToChannels(2))
+    assert data.shape[1] == 2
+    data2 = arr(Signal(data, 22 * Hz) >> ToChannels(1))
+    assert data2.shape[1] == 1 and np.array_equal(data2, data.sum(axis=1, keepdims=True))     # sum, not mean
+    with pytest.raises(SignalError):
+        tone >> ToChannels(2) >> ToChannels(3)
+
+
+def test_automatic_reformatting():                                # runtests.jl:461-470
+    a = Signal(sin, 200 * Hz, ω=10 * Hz) >> ToChannels(2) >> Until(5 * s)
+    b = Signal(sin, 100 * Hz, ω=5 * Hz) >> Until(3 * s)
+    mixed = Mix(a, b)
+    assert nchannels(mixed) == 2 and mixed.framerate == 200
+    assert arr(mixed).shape[0] == 1000
+    assert arr(Mix(a, b, 1)).shape[0] == 1000
+
+
+@pytest.mark.parametrize("nch", [1, 2])
+def test_empty_and_infinite_signals(nch):                         # runtests.jl:481-488, 550-575
+    tone = Signal(sin, 200 * Hz, ω=10 * Hz) >> ToChannels(nch) >> Until(10 * frames) >> Until(0 * frames)
+    assert nframes(tone) == 0 and arr(tone).shape == (0, nch)
+    assert nframes(OperateOn(np.negative, tone)) == 0
+    tone = Signal(sin, 200 * Hz, ω=10 * Hz) >> ToChannels(nch) >> Until(10 * frames) >> After(5 * frames) >> After(2 * frames)
+    assert nframes(tone) == 3 and arr(tone).shape == (3, nch)
+    for mk in (lambda: Signal(sin, 200 * Hz, ω=10 * Hz) >> ToChannels(nch) >> After(5 * frames) >> Until(5 * frames),
+               lambda: Signal(sin, 200 * Hz, ω=10 * Hz) >> ToChannels(nch) >> Until(10 * frames) >> After(5 * frames)):
+        tone = mk()
+        assert nframes(tone) == 5
+        got = arr(tone)
+        assert got.shape == (5, nch) and got[0, 0] > 0.9           # frame 6 of a 10 Hz tone at 200 Hz
+    with pytest.raises(SignalError):
+        oracle.sink(Signal(sin, 200 * Hz) >> Normpower >> Until(1 * s))
+    with pytest.raises(SignalError):
+        oracle.sink(Signal(sin, 200 * Hz) >> ToChannels(nch))
+
+
+def test_frame_units():                                           # runtests.jl:602-614
+    rng = np.random.default_rng(3)
+    x = Signal(rng.random((100, 2)), 10 * Hz)
+    y = Signal(rng.random((50, 2)), 10 * Hz)
+    assert arr(x >> Until(30 * frames)).shape[0] == 30
+    assert arr(x >> After(30 * frames)).shape[0] == 70
+    assert arr(x >> Append(y) >> After(20 * frames)).shape[0] == 130
+    assert arr(x >> Append(y) >> Until(130 * frames)).shape[0] == 130
+    assert arr(x >> Pad(zero) >> Until(150 * frames)).shape[0] == 150
+    assert arr(x >> Ramp(10 * frames)).shape[0] == 100
+    assert arr(x >> FadeTo(y, 10 * frames)).shape[0] > 100
