@@ -354,3 +354,22 @@ def test_frame_units():                                           # runtests.jl:
     assert arr(x >> Pad(zero) >> Until(150 * frames)).shape[0] == 150
     assert arr(x >> Ramp(10 * frames)).shape[0] == 100
     assert arr(x >> FadeTo(y, 10 * frames)).shape[0] > 100
+
+
+@pytest.mark.parametrize("nch", [1, 2])
+def test_arrays_as_signals(nch):                                  # runtests.jl:527-535
+    ramp10 = 10.0 * np.arange(1, 11)
+    tone = arr(Signal(sin, 200 * Hz, ω=10 * Hz) >> ToChannels(nch) >> Until(10 * frames) >> Mix(ramp10))
+    assert np.all(tone[:10, :] >= ramp10[:, None] - 1.0) and tone.shape == (10, nch)
+    x = arr(Signal(ramp10, 5 * Hz) >> ToChannels(nch) >> Until(1 * s))
+    assert x.dtype == np.float64 and x.shape == (5, nch)
+    with pytest.raises(SignalError):
+        Signal(np.zeros((2, 2, 2)))                                # poorly shaped arrays, runtests.jl:546
+
+
+def test_readme_sound1_at_4khz():                                 # runtests.jl:896-900
+    sound1 = Signal(sin, ω=1 * kHz) >> Until(5 * s) >> Ramp() >> Normpower >> Amplify(-20 * dB)
+    data, fs = oracle.sink(sound1 >> ToFramerate(4 * kHz))
+    assert fs == 4000 and data.shape[0] == 4000 * 5 and np.mean(np.abs(data)) > 0
+    # Normpower then -20 dB: rms 0.1 (the ramp is inside the normalisation)
+    assert np.sqrt(np.mean(data ** 2)) == pytest.approx(0.1, rel=1e-12)
