@@ -91,3 +91,19 @@ def test_float32_batch(gpu, ninst, nch, n):
         want, _ = oracle.sink(chain(xs[k]))
         assert want.dtype == np.float32
         assert np.max(np.abs(a[k][0].astype(np.float64) - want)) <= 1e-5 * rms(want)
+
+
+def test_padded_input_through_the_tensor_map_kernel(gpu):
+    """Pad(zero) |> Until |> Filt on a batch: the padded signal is materialised by an elementwise stage
+    and the tensor-map kernel filters that temporary (frame counts multiples of 16)."""
+    from signalops import frames
+    rng = np.random.default_rng(21)
+    xs = [rng.standard_normal((32000, 2)) for _ in range(16)]
+    chain = lambda x: Signal(x, 48 * kHz) >> Pad(zero) >> Until(48000 * frames) >> Filt(Lowpass, 4 * kHz, order=8) >> Amplify(-3 * dB)   # noqa: E731
+    a = run(gpu, [chain(x) for x in xs], tmap=True)
+    b = run(gpu, [chain(x) for x in xs], tmap=False)
+    for k in range(16):
+        assert a[k][0].shape == (48000, 2)
+        assert np.max(np.abs(a[k][0] - b[k][0])) <= 1e-12 * rms(b[k][0])
+    want, _ = oracle.sink(chain(xs[7]))
+    assert np.max(np.abs(a[7][0] - want)) <= F64_TOL * rms(want)
