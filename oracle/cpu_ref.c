@@ -60,11 +60,28 @@ typedef struct {
     const double* pfb;      /* Julia layout pfb[row + col*taps_per_phi]; h reversed for standard/decimator */
     const double* dpfb;
     double* history;        /* taps_per_phi-1 samples                    */
+    int32_t simd;           /* 1: dot products reassociate into 8 lanes like DSP.jl's `@simd` loops
+                               (the timing baseline); 0: strict left-to-right sums (the parity checker) */
 } oracle_fir;
 
-/* unsafe_dot(pfb, col, history, x, xLastIdx) / unsafe_dot(pfb, col, x, xLastIdx); 1-based xLastIdx */
-static double dot_window(const double* a, int64_t alen, const double* hist, const double* x, int64_t last) {
+/* DSP.jl's unsafe_dot loops carry `@simd`, i.e. the compiler may reassociate the sum into vector
+ * lanes (SURVEY.md §8c iii).  The timed CPU baseline does the same: eight partial sums, one clone per
+ * instruction set picked at load time, so the baseline is not handicapped by a scalar dependency chain. */
+__attribute__((target_clones("avx512f", "avx2", "default")))
+static double dot_lanes(const double* a, const double* w, int64_t n) {
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t i = 0;
+    for (; i + 8 <= n; i += 8)
+        for (int j = 0; j < 8; ++j) acc[j] += a[i + j] * w[i + j];
     double d = 0.0;
+    for (; i < n; ++i) d += a[i] * w[i];
+    return (((acc[0] + acc[4]) + (acc[1] + acc[5])) + ((acc[2] + acc[6]) + (acc[3] + acc[7]))) + d;
+}
+
+/* unsafe_dot(pfb, col, history, x, xLastIdx) / unsafe_dot(pfb, col, x, xLastIdx); 1-based xLastIdx */
+static double dot_window(const double* a, int64_t alen, const double* hist, const double* x, int64_t last, int simd) {
+    double d = 0.0;
+    if (simd && last >= alen) return dot_lanes(a, x + (last - alen), alen);
     if (last < alen) {
         const int64_t nh = alen - last;              /* taken from the end of history (length alen-1) */
         const double* h = hist + (alen - 1 - nh);
@@ -102,8 +119,8 @@ int64_t oracle_fir_filt(double* buf, int64_t buflen, oracle_fir* k, const double
             if (out >= buflen) return -1;
             const double* p = k->pfb + (int64_t)(k->phi_idx - 1) * T;
             const double* dp = k->dpfb + (int64_t)(k->phi_idx - 1) * T;
-            const double lower = dot_window(p, T, k->history, x, k->x_idx);
-            const double upper = dot_window(dp, T, k->history, x, k->x_idx);
+            const double lower = dot_window(p, T, k->history, x, k->x_idx, k->simd);
+            const double upper = dot_window(dp, T, k->history, x, k->x_idx, k->simd);
             buf[out++] = lower + upper * k->alpha;
             /* update(kernel) */
             k->phi_acc += k->delta;
@@ -119,7 +136,7 @@ int64_t oracle_fir_filt(double* buf, int64_t buflen, oracle_fir* k, const double
         int64_t idx = k->input_deficit;
         while (idx <= xlen) {
             if (out >= buflen) return -1;
-            buf[out++] = dot_window(k->pfb + (int64_t)(k->phi_idx - 1) * T, T, k->history, x, idx);
+            buf[out++] = dot_window(k->pfb + (int64_t)(k->phi_idx - 1) * T, T, k->history, x, idx, k->simd);
             idx += (k->phi_idx + k->decimation - 1) / k->interpolation;
             const int32_t v = k->phi_idx + k->phi_step;
             k->phi_idx = v > k->interpolation ? v - k->interpolation : v;
@@ -130,7 +147,7 @@ int64_t oracle_fir_filt(double* buf, int64_t buflen, oracle_fir* k, const double
         const int64_t step = k->kind == FIR_DECIMATOR ? k->decimation : 1;
         while (idx <= xlen) {
             if (out >= buflen) return -1;
-            buf[out++] = dot_window(k->pfb, T, k->history, x, idx);
+            buf[out++] = dot_window(k->pfb, T, k->history, x, idx, k->simd);
             idx += step;
         }
         k->input_deficit = idx - xlen;

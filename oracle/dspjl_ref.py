@@ -139,7 +139,7 @@ class FirState(C.Structure):
                 ("phi_step", C.c_int32), ("phi_idx", C.c_int32), ("input_deficit", C.c_int64),
                 ("x_idx", C.c_int64), ("rate", C.c_double), ("delta", C.c_double),
                 ("phi_acc", C.c_double), ("alpha", C.c_double), ("pfb", C.POINTER(C.c_double)),
-                ("dpfb", C.POINTER(C.c_double)), ("history", C.POINTER(C.c_double))]
+                ("dpfb", C.POINTER(C.c_double)), ("history", C.POINTER(C.c_double)), ("simd", C.c_int32)]
 
 
 def resample_filter(rate):

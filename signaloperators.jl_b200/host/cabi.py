@@ -86,8 +86,17 @@ def _check(lib, ctx, code):
 
 
 def dtype_code(dt):
+    """Sample type code of a host buffer handed to the C ABI: exactly the three types the device
+    reads and writes.  Anything else (Int32, Int16, ...) must be converted by the caller first —
+    silently treating it as Int64 would read or write past the array."""
     dt = np.dtype(dt)
-    return F32 if dt == np.float32 else F64 if dt == np.float64 else I64
+    if dt == np.float32:
+        return F32
+    if dt == np.float64:
+        return F64
+    if dt == np.int64:
+        return I64
+    raise TypeError(f"host buffers must be float32, float64 or int64, not {dt}")
 
 
 class Context:
@@ -156,6 +165,9 @@ class CompiledPlan:
             n, c = (a.shape[0], 1) if a.ndim == 1 else a.shape
             if a.ndim == 2 and c > 1 and not a.flags.f_contiguous:
                 raise ValueError("multi-channel host buffers must be column-major")
+            if n > 1 and a.strides[0] != a.itemsize:
+                raise ValueError("host buffers must be dense along time (stride of one element); "
+                                 "copy strided views with numpy.ascontiguousarray first")
             ld = n if a.ndim == 1 or c == 1 else a.strides[1] // a.itemsize
             bufs[k] = Buffer(a.ctypes.data, n, c, dtype_code(a.dtype), max(ld, n))
         return bufs

@@ -15,6 +15,7 @@ import numpy as np
 
 from . import cabi, graph as G
 from .lowering import Lowerer, np_dtype
+from .lowering import dtype_code as dtype_code_of
 
 
 class Array:
@@ -68,7 +69,16 @@ def _wrap(plan, data, to):
 
 
 def _colmajor(a):
-    return a if a.ndim == 1 or a.shape[1] == 1 or a.flags.f_contiguous else np.asfortranarray(a)
+    """Dense channel-planar view of `a` for the C ABI (element (n,c) at ptr[c*ld + n]): strided
+    1-D / (N,1) views (`x[::2]`, `stereo[:,0]` of a C-ordered array, `x[::-1]`) and C-ordered
+    matrices are copied; anything already dense in Julia's column-major layout is passed as is."""
+    if a.ndim == 1 or a.shape[1] == 1:
+        return a if a.size <= 1 or a.strides[0] == a.itemsize else np.ascontiguousarray(a)
+    return a if a.flags.f_contiguous else np.asfortranarray(a)
+
+
+# sample types the plan can write straight into the caller's array
+_DIRECT_RESULT_DTYPES = (np.dtype(np.float32), np.dtype(np.float64), np.dtype(np.int64))
 
 
 def sink(x=None, to=None):
@@ -105,16 +115,29 @@ def sink_into(result, x, to):
         raise G.SignalError(f"Signal is too short to fill buffer of length {n}.")
     lw = Lowerer()
     x = G.ToChannels(x, nch)
+    # The reference's `sink!` accepts any result eltype (each frame is converted on assignment).
+    # The device writes Float32/Float64/Int64; every other eltype (Int32, Int16, UInt8, Bool, ...) is
+    # sunk in the signal's own sample type and converted on the host.
+    direct = result.dtype in _DIRECT_RESULT_DTYPES
+    plan_dtype = result.dtype if direct else np_dtype(dtype_code_of(x.sampletype))
     # the plan covers only the requested prefix, so infinite signals are fine here
-    plan = _build_prefix(lw, x, n, result.dtype)
-    if result.ndim == 2 and nch > 1 and not result.flags.f_contiguous:
-        tmp = np.empty(result.shape, dtype=result.dtype, order="F")
-        cp = to.compiled(plan.tobytes())
-        to.last_stats = cp.run_host(1, [_colmajor(a) for a in plan.input_arrays], [tmp])
-        result[...] = tmp
-    elif n > 0:
-        cp = to.compiled(plan.tobytes())
+    plan = _build_prefix(lw, x, n, plan_dtype)
+    if n == 0:
+        return result
+    cp = to.compiled(plan.tobytes())
+    dense = _colmajor(result) is result
+    if direct and dense:
         to.last_stats = cp.run_host(1, [_colmajor(a) for a in plan.input_arrays], [result])
+    else:
+        # strided / C-ordered / narrow-integer results: run into a dense temporary and copy back
+        tmp = np.empty(result.shape, dtype=plan_dtype, order="F")
+        to.last_stats = cp.run_host(1, [_colmajor(a) for a in plan.input_arrays], [tmp])
+        if direct or np.dtype(plan_dtype).kind in "iu":
+            result[...] = tmp
+        else:
+            if result.dtype.kind in "iub" and not np.all(tmp == np.trunc(tmp)):
+                raise G.SignalError(f"InexactError: cannot convert non-integral samples to {result.dtype}")
+            result[...] = tmp.astype(result.dtype)
     return result
 
 

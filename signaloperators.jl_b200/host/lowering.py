@@ -245,6 +245,10 @@ class Lowerer:
             m = m.astype(np.int64)
         elif m.dtype not in (np.float32, np.float64):
             m = m.astype(np.float64)
+        # strided views (x[::2], stereo[:,0] of a C-ordered array, x[::-1]) become dense copies here:
+        # the C ABI only describes rows that are contiguous in time
+        if m.shape[0] > 1 and m.strides[0] != m.itemsize:
+            m = np.asfortranarray(m) if m.shape[1] > 1 else np.ascontiguousarray(m)
         k = len(self.plan.inputs)
         self.plan.inputs.append(BufDesc(m.shape[0], m.shape[1], dtype_code(m.dtype)))
         self.plan.input_arrays.append(m)

@@ -27,7 +27,7 @@ def test_reference_arm_prints_one_contract_line():
               "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f64"
-    assert "workload" in d["config"] and d["config"]["workload"].startswith("cfg2")
+    assert "workload" in d["config"] and d["config"]["workload"].startswith("cfg3")
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
