@@ -44,9 +44,10 @@
 // ~110 cycles per copy): the per-row copies are bound by the TMA unit's issue rate, which only fewer,
 // larger copies (a tensor map over all rows) would lift.
 //
-// Eligibility (checked by the host): Float64 in/out, 16-byte aligned rows, no epilogue
-// program (the sum of squares for a following Normpower is supported).  Everything else
-// takes k_fir.cuh.
+// Eligibility (checked by the host): Float64 in/out, 16-byte aligned rows, epilogue = none or a
+// constant gain (folded into the taps; the sum of squares for a following Normpower is
+// supported).  Everything else takes k_fir.cuh.  Batches whose rows sit at base + row*stride take
+// k_fir_tmap.cuh instead (tensor-map loads and stores).
 #pragma once
 #include "interp.cuh"
 #include "k_iir_tma.cuh"   // mbarrier / bulk-copy helpers
@@ -79,6 +80,7 @@ struct FirMmaParams {
     const double* alpha;    // [m] fractional phase (0 for the rational kernels)
     long long* dbg;         // optional [gridDim.x * gridDim.y][8] cycle counters (tuning aid), or nullptr
     int tab_doubles;        // nphases*tapsper: both banks are copied to shared memory
+    double gain;            // constant-gain epilogue folded into the taps (1.0 = none)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -263,6 +265,12 @@ k_fir_mma(const __grid_constant__ FirMmaParams P) {
 #pragma unroll
                         for (int j = 0; j < 2; ++j) pv[n][j] = fma(al[n], dv[n][j], pv[n][j]);
                 }
+                if (P.gain != 1.0) {
+#pragma unroll
+                    for (int n = 0; n < NPW; ++n)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) pv[n][j] *= P.gain;
+                }
 #pragma unroll
                 for (int n = 0; n < NPW; ++n)
 #pragma unroll
@@ -283,6 +291,7 @@ k_fir_mma(const __grid_constant__ FirMmaParams P) {
                         if (k >= lo && k < hi) {
                             h = pf_tab[off + k];
                             if (dpf_tab) h = fma(alpha, dpf_tab[off + k], h);
+                            h *= P.gain;
                         }
                         band[k * kFmHbPitch + n] = h;
                     }

@@ -61,6 +61,21 @@ bool iir_tmap_encode(void* out_map, void* base, int64_t frames, int64_t rows, in
     return r == CUDA_SUCCESS;
 }
 
+// [rows][dim0] matrix of Float64 samples, row r at base + r*row_stride_bytes; box = (box0 samples, box1 rows),
+// 128-byte swizzle (box0*8 <= 128), zero fill outside the tensor.  Used by k_fir_tmap.
+bool tmap_encode_2d_f64(void* out_map, void* base, int64_t dim0, int64_t rows, int64_t row_stride_bytes, int box0, int box1) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn || dim0 < 1 || rows < 1 || box0 * 8 > 128 || box1 > 256 || (row_stride_bytes & 15) || ((uintptr_t)base & 15)) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)dim0, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)row_stride_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = fn((CUtensorMap*)out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 void launch_iir_tmap(bool f32, int M, bool unitb, dim3 grid, cudaStream_t st, const IirTmapParams& P, const void* map_in,
                      const void* map_out) {
     const CUtensorMap& a = *(const CUtensorMap*)map_in;

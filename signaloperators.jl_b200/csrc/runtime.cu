@@ -27,6 +27,7 @@
 #include "k_iir_carry.cuh"
 #include "k_fir.cuh"
 #include "k_fir_mma.cuh"
+#include "k_fir_tmap.cuh"
 #include "k_iir_tmap.cuh"
 #include "k_map.cuh"
 
@@ -158,6 +159,8 @@ struct FirDerived {
     int ring32 = 0;              // k_fir_mma: positions resident while a tile is multiplied and the next two are loaded
     int in_buf = -1;
     int64_t in_len = 0;
+    bool epi_const = true;       // epilogue = none or LOAD STAGE (MUL CONST){1,2}: folded into the taps
+    double epi_scale = 1.0;
 };
 
 struct StageRT {
@@ -406,6 +409,7 @@ void derive_iir(sigops_plan& p, StageRT& s, int idx) {
 
 constexpr size_t kFirSmemLimit = 200 * 1024;
 constexpr size_t kFirMmaSmemLimit = 220 * 1024;
+constexpr size_t kFirTmSmemLimit = 232448 - 512;   // 227 KB per block minus the kernel's static barriers
 constexpr int kFirT = 64;     // table padding granularity (largest tile)
 
 // k_fir<G> geometry: merged-tap rows, window pitch and dynamic shared memory
@@ -446,6 +450,18 @@ void derive_fir(sigops_plan& p, StageRT& s, int idx) {
         fail(SIGOPS_ERR_UNSUPPORTED, "%s: input must be a bare zero-padded buffer load", what);
     s.fir.in_buf = I.buf;
     s.fir.in_len = I.i1;
+    s.fir.epi_const = st.epi_prog_len == 0;
+    if (st.epi_prog_len >= 2 && st.epi_prog_len <= 3) {
+        const sigops_instr* E = &p.instrs[st.epi_prog_start];
+        bool ok = E[0].op == SIGOPS_OP_LOAD && E[0].leaf == SIGOPS_LEAF_STAGE;
+        double sc = 1.0;
+        for (int i = 1; i < st.epi_prog_len && ok; ++i) {
+            ok = E[i].op == SIGOPS_OP_MUL && E[i].leaf == SIGOPS_LEAF_CONST;
+            sc *= E[i].d0;
+        }
+        s.fir.epi_const = ok;
+        if (ok) s.fir.epi_scale = sc;
+    }
 
     // Replay the kernel's index recurrence (DSP.jl stream_filt.jl `filt!`/`update`).
     const int64_t nout = st.n_out;
@@ -1039,14 +1055,112 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
             P.pfb = pd.blob + p.tables[g.pfb_table].offset;
             P.dpfb = g.dpfb_table >= 0 ? pd.blob + p.tables[g.dpfb_table].offset : nullptr;
             P.xi0 = pd.xi0[si]; P.phi = pd.phi[si];
-            // Tensor-core path: plain Float64 rows on 16-byte boundaries, no epilogue program
-            bool mma = g.epi_prog_len == 0 && !getenv("SIGOPS_NO_FIR_MMA") &&
+            // Tensor-core paths: plain Float64 rows on 16-byte boundaries, epilogue = none or a constant gain
+            bool mma = s.fir.epi_const && !getenv("SIGOPS_NO_FIR_MMA") &&
                        p.bufs[s.fir.in_buf].dtype == SIGOPS_F64 && p.bufs[g.out_buf].dtype == SIGOPS_F64;
             for (int64_t i = 0; i < ninst && mma; ++i)
                 for (int b : {s.fir.in_buf, (int)g.out_buf}) {
                     const BufRef& rb = ((const BufRef*)slot.last_table.data())[i * nbuf + b];
                     if (((uintptr_t)rb.ptr & 15) || (rb.nch > 1 && (rb.ld & 1)) || rb.dtype != SIGOPS_F64) mma = false;
                 }
+            const int64_t tabd_ = (int64_t)g.n_phases * g.taps_per_phase;
+            // Tensor-map kernel (k_fir_tmap.cuh): every row of the wave at base + row*stride, more than 64 rows,
+            // band <= 64 positions, a tile's window inside the ring
+            if (mma && rows > 64 && !getenv("SIGOPS_NO_FIR_TMAP") && iir_tmap_available() && rows < (int64_t(1) << 31) &&
+                g.n_out < (int64_t(1) << 31) && s.fir.in_len < (int64_t(1) << 31)) {
+                const BufRef* refs = (const BufRef*)slot.last_table.data();
+                auto uniform = [&](int b, char*& base, int64_t& stride) {
+                    const BufRef& r0 = refs[b];
+                    base = (char*)r0.ptr;
+                    stride = r0.ld * 8;
+                    if ((stride & 15) || ((uintptr_t)base & 15)) return false;
+                    for (int64_t i = 0; i < ninst; ++i) {
+                        const BufRef& rb = refs[i * nbuf + b];
+                        if (rb.ld != r0.ld || rb.nch != r0.nch || (char*)rb.ptr != base + (int64_t)i * r0.nch * stride) return false;
+                    }
+                    return true;
+                };
+                char *bin = nullptr, *bout = nullptr;
+                int64_t sin_ = 0, sout = 0;
+                const int ks = (int)round_up(s.fir.dpad + g.taps_per_phase, 4);
+                const int win_slots = (s.fir.pmax32 + 14) / 16 + 1;          // worst alignment of a tile's window
+                int nslot = kFtMaxSlots;
+                const bool has_d = P.dpfb != nullptr;
+                while (nslot > win_slots + 1 && fir_tm_smem_bytes(nslot, ks, (int)tabd_, has_d) > kFirTmSmemLimit) --nslot;
+                if (const char* e = getenv("SIGOPS_FIR_NSLOT")) nslot = std::max(win_slots + 1, std::min(kFtMaxSlots, atoi(e)));
+                TensorMapBlob mi, mo;
+                if (ks <= kFtMaxKs && nslot >= win_slots + 1 && fir_tm_smem_bytes(nslot, ks, (int)tabd_, has_d) <= kFirTmSmemLimit &&
+                    uniform(s.fir.in_buf, bin, sin_) && uniform(g.out_buf, bout, sout) && s.fir.in_len >= 1 &&
+                    tmap_encode_2d_f64(&mi, bin, s.fir.in_len, rows, sin_, kFtSlotPos, kFtRows) &&
+                    tmap_encode_2d_f64(&mo, bout, g.n_out, rows, sout, 16, kFtRows)) {
+                    FirTmParams T{};
+                    T.scalars = scalars; T.nscalars = nscal; T.sumsq_slot = g.sumsq_slot; T.nch = g.nchannels;
+                    T.nrows = rows; T.n_out = g.n_out; T.tapsper = g.taps_per_phase; T.ks = ks; T.nslot = nslot;
+                    T.ntiles = (g.n_out + kFmT - 1) / kFmT;
+                    T.pfb = P.pfb; T.dpfb = P.dpfb; T.xi0 = P.xi0; T.poff = pd.poff[si]; T.alpha = pd.alpha[si];
+                    T.tab_doubles = (int)tabd_;
+                    T.gain = s.fir.epi_scale;
+                    if (const char* e = getenv("SIGOPS_FIR_EXP")) T.exp = atoi(e);
+                    const int64_t groups = (rows + kFtRows - 1) / kFtRows;
+                    // segments along the time axis: whole waves of one block per SM; a segment pays about
+                    // three tiles of start-up (first window, pipeline fill)
+                    int64_t best_tps = T.ntiles;
+                    double best_cost = 1e300;
+                    for (int w = 1; w <= 8; ++w) {
+                        int64_t nseg = std::max<int64_t>(1, std::min<int64_t>(T.ntiles, ((int64_t)w * dev.sm_count + groups - 1) / groups));
+                        const int64_t tps = (T.ntiles + nseg - 1) / nseg;
+                        nseg = (T.ntiles + tps - 1) / tps;
+                        const int64_t waves = (groups * nseg + dev.sm_count - 1) / dev.sm_count;
+                        const double cost = (double)waves * (double)(tps + 3);
+                        if (cost < best_cost) { best_cost = cost; best_tps = tps; }
+                    }
+                    if (const char* e = getenv("SIGOPS_FIR_TPS")) best_tps = std::max<int64_t>(1, atoll(e));
+                    T.tiles_per_seg = best_tps;
+                    const int64_t nseg = (T.ntiles + best_tps - 1) / best_tps;
+                    const size_t smem = fir_tm_smem_bytes(nslot, ks, (int)tabd_, has_d);
+                    dim3 tgrid((unsigned)nseg, (unsigned)groups);
+                    if (groups <= 65535) {
+                        if (getenv("SIGOPS_DEBUG"))
+                            fprintf(stderr, "[sigops] FIR stage %zu: tensor-map rows=%lld n_out=%lld taps=%d ks=%d slots=%d (window %d) grid=%lldx%lld tiles/seg=%lld smem=%zu gain=%g\n",
+                                    si, (long long)rows, (long long)g.n_out, T.tapsper, ks, nslot, win_slots, (long long)nseg, (long long)groups,
+                                    (long long)best_tps, smem, T.gain);
+                        const bool ssq = g.sumsq_slot >= 0;
+                        if (getenv("SIGOPS_FIR_DBG")) {
+                            // tuning aid: one synchronous launch with cycle counters, printed per role
+                            const size_t nb = (size_t)nseg * groups;
+                            long long* dbg = nullptr;
+                            CUDA_OK(cudaMalloc(&dbg, nb * 8 * sizeof(long long)));
+                            CUDA_OK(cudaMemset(dbg, 0, nb * 8 * sizeof(long long)));
+                            FirTmParams D = T;
+                            D.dbg = dbg;
+                            ensure_dyn_smem(k_fir_tmap<false>, smem);
+                            k_fir_tmap<false><<<tgrid, kFtThreads, smem, stream>>>(D, *(const CUtensorMap*)&mi, *(const CUtensorMap*)&mo);
+                            CUDA_OK(cudaStreamSynchronize(stream));
+                            std::vector<long long> h(nb * 8);
+                            CUDA_OK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+                            cudaFree(dbg);
+                            double sum[8] = {0};
+                            for (size_t b = 0; b < nb; ++b)
+                                for (int k = 0; k < 8; ++k) sum[k] += (double)h[b * 8 + k];
+                            const double per = 1.0 / ((double)nb * (double)best_tps);
+                            fprintf(stderr, "[sigops] FIR tmap cycles/tile  compute: wait_taps %.0f wait_full %.0f wait_stg %.0f total %.0f | helper: wait_done %.0f build %.0f\n",
+                                    sum[0] * per, sum[1] * per, sum[2] * per, sum[3] * per, sum[4] * per, sum[5] * per);
+                        }
+                        add(KIND_FIR, [=](cudaStream_t st) {
+                            const CUtensorMap& a = *(const CUtensorMap*)&mi;
+                            const CUtensorMap& b = *(const CUtensorMap*)&mo;
+                            if (ssq) {
+                                ensure_dyn_smem(k_fir_tmap<true>, smem);
+                                k_fir_tmap<true><<<tgrid, kFtThreads, smem, st>>>(T, a, b);
+                            } else {
+                                ensure_dyn_smem(k_fir_tmap<false>, smem);
+                                k_fir_tmap<false><<<tgrid, kFtThreads, smem, st>>>(T, a, b);
+                            }
+                        });
+                        continue;
+                    }
+                }
+            }
             if (mma) {
                 FirMmaParams Q{};
                 Q.bufrefs = d_refs; Q.scalars = scalars; Q.nbuf = nbuf; Q.nscalars = nscal;
@@ -1058,6 +1172,7 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                 Q.pitch = Q.ring + ((4 - Q.ring % 16) + 16) % 16;
                 Q.pfb = P.pfb; Q.dpfb = P.dpfb; Q.xi0 = P.xi0; Q.poff = pd.poff[si]; Q.alpha = pd.alpha[si];
                 Q.ntiles = (g.n_out + kFmT - 1) / kFmT;
+                Q.gain = s.fir.epi_scale;
                 // both polyphase banks ride along in shared memory when that leaves the ring its room
                 const int64_t tabd = (int64_t)g.n_phases * g.taps_per_phase;
                 const size_t tab_bytes = (size_t)tabd * 8 * (P.dpfb ? 2 : 1);

@@ -721,9 +721,13 @@ class Lowerer:
                     # writes straight into the copy's destination)
                     if prod.kind == STAGE_MAP and not bare_copy:
                         continue
-                    # resamplers keep a bare store: that is what the tensor-core kernel takes, and a
-                    # separate elementwise pass over its output costs far less than the scalar FIR kernel
-                    if prod.kind == STAGE_FIR and not bare_copy:
+                    # resamplers take a bare store or a constant gain (`ToFramerate |> Amplify(c)`: the
+                    # tensor-core kernels fold it into the taps); anything richer stays a separate
+                    # elementwise pass, which costs far less than the scalar FIR kernel
+                    const_gain = (2 <= len(pc.prog) <= 3 and pc.prog[0].op == OP_LOAD and all(
+                        I.op == OP_MUL and I.leaf == LEAF_CONST for I in pc.prog[1:]) and
+                        self._desc(st.out_buf).dtype == self._desc(tag).dtype == F64)
+                    if prod.kind == STAGE_FIR and not (bare_copy or const_gain):
                         continue
                     uses = [I for I in refs if I.buf == tag]
                     elsewhere = any(I.leaf in (LEAF_BUF, LEAF_CHANSUM) and I.buf == tag

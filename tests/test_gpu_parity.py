@@ -331,3 +331,53 @@ def test_errors(gpu):
         sink(Signal(sin, 200 * Hz) >> Normpower >> Until(1 * s), gpu)
     with pytest.raises(SignalError):
         sink_into(np.ones((10, 2)), np.ones((5, 2)), gpu)
+
+
+# ---- host arrays that are not dense (strides must not be ignored) -----------------
+
+def test_strided_views_are_read_through_their_strides(gpu):
+    x = rng(21).standard_normal(4000)
+    st = rng(22).standard_normal((2000, 2))                 # C-ordered: st[:, 0] has a stride of 2 samples
+    check(gpu, lambda: Signal(x[::2], 1 * kHz) >> Filt(Lowpass, 100 * Hz))
+    check(gpu, lambda: Signal(x[::-1], 1 * kHz) >> Amplify(-6 * dB), tol=1e-12)
+    check(gpu, lambda: Signal(st[:, 0], 1 * kHz) >> Mix(Signal(st[:, 1], 1 * kHz)), tol=1e-12)
+    check(gpu, lambda: Signal(st[::3], 1 * kHz) >> Filt(Highpass, 50 * Hz))
+    got = sink(Signal(x[::2], 1 * kHz), gpu)[0]
+    assert np.array_equal(got[:, 0], x[::2])
+
+
+def test_sink_into_strided_and_narrow_results(gpu):
+    sig = Signal(np.arange(20.0), 10 * Hz)
+    parent = np.full(40, -1.0)
+    view = parent[::2]
+    sink_into(view, sig, gpu)
+    assert np.array_equal(view, np.arange(20.0)) and np.all(parent[1::2] == -1.0)      # neighbours untouched
+    for dt in (np.int32, np.int16, np.uint8):
+        guard = np.full(30, 7, dtype=dt)
+        res = guard[5:25]
+        sink_into(res, Signal(np.arange(20), 10 * Hz), gpu)
+        assert np.array_equal(res, np.arange(20).astype(dt))
+        assert np.all(guard[:5] == 7) and np.all(guard[25:] == 7)                      # no write past the result
+    r32 = np.zeros(20, dtype=np.int32)
+    sink_into(r32, sig, gpu)                                                           # integral floats convert
+    assert np.array_equal(r32, np.arange(20))
+    from signalops import SignalError
+    with pytest.raises(SignalError):                                                   # Julia: InexactError
+        sink_into(np.zeros(20, dtype=np.int32), Signal(np.arange(20.0) + 0.5, 10 * Hz), gpu)
+    m = np.zeros((20, 2), dtype=np.float32)[:, ::-1]                                   # negative channel stride
+    sink_into(m, Signal(np.arange(40.0).reshape(20, 2), 10 * Hz), gpu)
+    assert np.array_equal(m, np.arange(40.0).reshape(20, 2).astype(np.float32))
+
+
+# ---- raw filter objects: Filt(h) with DSP.jl coefficient types (src/filters.jl:65,89-95) --------
+
+def test_raw_filter_objects(gpu):
+    from signalops import Biquad, Butterworth, PolynomialRatio, digitalfilter
+    x = rng(31).standard_normal((3000, 2))
+    h = digitalfilter(Highpass(8, fs=100), Chebyshev1(5, 1))
+    a = check(gpu, lambda: Signal(x, 100 * Hz) >> Filt(h))
+    b = check(gpu, lambda: Signal(x, 100 * Hz) >> Filt(Highpass, 8 * Hz, method=Chebyshev1(5, 1)))
+    assert np.max(np.abs(a[0] - b[0])) <= 1e-12 * rms(b[0])                           # runtests.jl:364-368
+    check(gpu, lambda: Signal(x, 100 * Hz) >> Filt(digitalfilter(Lowpass(20, fs=100), Butterworth(4))))
+    check(gpu, lambda: Signal(x, 100 * Hz) >> Filt(Biquad(0.2, 0.3, 0.1, -0.5, 0.25)))
+    check(gpu, lambda: Signal(x, 100 * Hz) >> Filt(PolynomialRatio([0.3, 0.2], [1.0, -0.4, 0.1])))
