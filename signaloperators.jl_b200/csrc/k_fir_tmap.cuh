@@ -19,7 +19,10 @@
 //   * finished 32-output tiles are staged in shared memory (two 16-output swizzled boxes) and
 //     written with two `cp.async.bulk.tensor.2d` stores by a store thread (whole 128-byte lines;
 //     columns past n_out and rows past the last are clipped by the tensor bounds);
-//   * the compute warps do nothing but LDS + DMMA + 8 shared-memory stores per tile.
+//   * the compute warps do nothing but LDS + DMMA + 16 shared-memory stores per tile.  Shared-memory
+//     bandwidth is the co-critical resource (ncu on the first version: LSU wavefronts + TMA traffic busy 70 %
+//     of the time, tensor pipe 66 %), so the k axis is walked in ring-aligned blocks of 4 positions whose A
+//     fragments are shared by all four output groups of the tile.
 // A fragment rows are taken in bit-reversed order (fragment row r -> signal row {0,4,2,6,1,5,3,7}[r])
 // which makes both the swizzled A-fragment loads (any position alignment) and the staging stores
 // bank-conflict free.  The tap bands live at pitch 8 with an XOR on the column index (conflict-free
@@ -27,9 +30,9 @@
 // the staged banks: g*(sum h x) becomes sum (g h) x, a rounding-level difference.  Groups whose eight outputs span fewer positions skip
 // the last k-step (44.1 -> 48 kHz: 11.4 instead of 12 on average).
 //
-// Block = 16 warps in four warpgroups that re-balance their registers with setmaxnreg: 8 compute (4 output
-// groups x 2 row halves, 176 registers), 4 helpers (tap bands, one per group), 1 producer (ring loads),
-// 1 store.  Barriers: full[slot], done[tile&3] (compute warps), taps[tile&1],
+// Block = 16 warps in four warpgroups that re-balance their registers with setmaxnreg: 8 compute (two per
+// sub-partition; each 8/G row fragments x G output groups, 176 registers), 4 helpers (tap bands, one per
+// group), 1 producer (ring loads), 1 store.  Barriers: full[slot], done[tile&3] (compute warps), taps[tile&1],
 // stg_full / stg_free (staging hand-over).
 //
 // Eligibility (host): Float64 in/out, every row of the wave at base + row*stride with 16-byte
@@ -68,9 +71,10 @@ struct FirTmParams {
     const double* alpha;    // [m] fractional phase
     int tab_doubles;
     double gain;            // folded into the taps
+    int aligned;            // 1: band row 0 = the group's first window position rounded down to a multiple of 4 ring
+                            //    positions (compute warps share A blocks between groups, G > 1); 0: exactly that position
     long long* dbg;         // optional [blocks][8] cycle counters (tuning aid, SIGOPS_FIR_DBG=1), or nullptr
-    int exp;                // tuning experiments (SIGOPS_FIR_EXP bit mask; results are wrong when set): 1 no staging
-                            // stores, 2 no tensor stores, 4 no A-operand loads in the k-loop, 8 no DMMAs
+    int exp;                // tuning experiments (SIGOPS_FIR_EXP bit mask; wrong results): 1 no staging stores, 2 no tensor stores
 };
 
 inline size_t fir_tm_smem_bytes(int nslot, int ks, int tab_doubles, bool has_dpfb) {
@@ -100,7 +104,7 @@ __device__ __forceinline__ void sts_v2f64(unsigned a, double x, double y) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
 }
 
-template <bool SSQ>
+template <bool SSQ, int G>
 __global__ void __launch_bounds__(kFtThreads, 1)
 k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtensorMap tm_in,
            const __grid_constant__ CUtensorMap tm_out) {
@@ -146,105 +150,153 @@ k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtens
     const unsigned band_tile = 4u * (unsigned)P.ks * 64u;      // bytes per band buffer
 
     if (warp < kFtNCW) {
-        // ---------------- DMMA ----------------
+        // ---------------- DMMA: a warp owns F = 8/G row fragments (8F rows) x G consecutive output groups of the tile ----------------
+        // The k axis is walked in blocks of 4 positions aligned to the ring (position mod 4 == 0): the A
+        // fragments of a block are loaded once and feed every group of the warp whose band covers the block.
+        // Two compute warps per sub-partition: a single one cannot hide its own index arithmetic and operand
+        // loads behind its DMMAs (measured with 4 warps x 16 fragments: 39 cycles per DMMA instead of 16).
+        constexpr int F = 8 / G;
+        const int gw = warp % (4 / G), rw = warp / (4 / G);
+        const int g0 = G * gw;                                           // my first output group
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kFtRegsCompute));
-        const int g = warp & 3, half = warp >> 2;
         const int kk = lane & 3, rr = lane >> 2;
         const int rmap = ((rr & 1) << 2) | (rr & 2) | (rr >> 2);        // 3-bit reversal
-        const int rloc = half * 64 + rmap;                               // fragment i holds row rloc + 8i
+        const int rloc = rw * (8 * F) + rmap;                            // fragment i holds row rloc + 8i
         const unsigned key0 = (unsigned)rmap << 4;                       // swizzle: 16-byte chunk ^= row & 7
-        const unsigned arow0 = ring + rloc * 128;
-        const unsigned srow0 = stg + (g >> 1) * 16384 + rloc * 128 + ((((g & 1) * 4 + kk) << 4) ^ key0);
         const int nn = rr ^ ((kk >> 1) << 2);                            // band column after the XOR
-        const int nks_max = P.ks >> 2;
         // (opaque to the optimiser: otherwise ptxas re-derives these from the thread index inside the k-loop —
-        //  S2R + a dozen integer instructions per k-step — instead of keeping three registers)
-        unsigned arow = arow0, key = key0, srow = srow0;
-        asm volatile("" : "+r"(arow), "+r"(key), "+r"(srow));
+        //  S2R + a dozen integer instructions per k-step — instead of keeping a few registers)
+        unsigned arow = ring + rloc * 128 + ((unsigned)(kk * 8) ^ key0);  // my element of block 0 of slot 0, swizzled
+        unsigned key = key0;
+        unsigned srow = stg + rloc * 128;
+        unsigned bcol = (unsigned)(kk * 64 + nn * 8);                    // my B element inside a 4-row band block
+        unsigned arow1 = ring + rloc * 128;                              // (G == 1) my row of slot 0
+        asm volatile("" : "+r"(arow), "+r"(key), "+r"(srow), "+r"(bcol), "+r"(arow1));
         double ssq[SSQ ? 8 : 1];
 #pragma unroll
         for (int i = 0; i < (SSQ ? 8 : 1); ++i) ssq[i] = 0.0;
 
-        int64_t xq_nx = __ldg(P.xi0 + t0 * kFmT + 8 * g);
-        int64_t x7_nx = __ldg(P.xi0 + t0 * kFmT + 8 * g + 7);
-        int64_t xe_nx = __ldg(P.xi0 + t0 * kFmT + kFmT - 1);
-        int64_t jwait = 0;                              // slots [0, jwait) have been waited for
-        int jw_slot = 0;
-        unsigned jw_par = 0;
-        int64_t jslot0 = 0;                             // global slot index behind `slot_t`
-        int slot_t = 0;
+        // index tables, read one tile ahead: first / last output of every group, last output of the tile
+        int64_t xq_nx[G], x7_nx[G];
+        auto fetch_idx = [&](int64_t t) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                xq_nx[g] = __ldg(P.xi0 + t * kFmT + 8 * (g0 + g));
+                x7_nx[g] = __ldg(P.xi0 + t * kFmT + 8 * (g0 + g) + 7);
+            }
+        };
+        fetch_idx(t0);
         long long dbg_acc[3] = {0, 0, 0};
 
-        // operand stream of the tile in flight: ring slot / byte offset in the 128-byte row of the k-step
-        // loaded last, band pointer, k-steps
-        int slot = 0, up = 0, nks = 0;
-        unsigned bp = 0;
-        // two operand sets: one feeds the DMMAs of a k-step while the other is being loaded for the next
-        double a0[8], b0, a1[8], b1;
+        // the tile in flight: first aligned block (global index and ring slot / quarter), blocks in all, and per
+        // group the first block and the number of blocks of its band
+        int64_t blk0 = 0;                               // global block index (position / 4 relative to pos_base) of the block loaded last
+        int slot = 0, sub = 0;                          // its ring slot and quarter of the slot (G == 1: per lane, byte offset in the row)
+        int64_t jcur = 0;                               // (G == 1) global slot index behind `slot`
+        int nbt = 0, ob[G], nb[G];
+        unsigned bandbase = 0;
+        struct Ops { double a[F], b[G]; };
+        Ops o0, o1;
 
-        // Set tile t up (index arithmetic, barrier waits) and load the operands of its first k-step into
-        // (a, b).  Runs underneath the last k-step of the tile before it.
-        auto setup = [&](int64_t t, double (&a)[8], double& b) {
+        auto load_ops = [&](Ops& o, int b, unsigned bb, const int (&obx)[G], const int (&nbx)[G]) {
+            // G > 1: blocks are ring-aligned, (slot, sub) are warp-uniform; low 7 address bits = (kk*8 ^ swizzle key)
+            // from `arow`, quarter of the slot in bits 5-6.  G == 1: the band starts at the group's own first
+            // window position, every lane tracks its own position (slot, byte offset `sub` in the 128-byte row).
+            const unsigned ap = G > 1 ? (arow + (unsigned)slot * kFtSlotBytes) ^ (unsigned)(sub << 5)
+                                      : arow1 + (unsigned)slot * kFtSlotBytes + ((unsigned)sub ^ key);
+#pragma unroll
+            for (int i = 0; i < F; ++i) o.a[i] = lds_f64(ap + i * 1024);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                int kb = b - obx[g];                    // clamped: groups that do not cover the block load a row they own anyway
+                kb = kb < 0 ? 0 : (kb >= nbx[g] ? nbx[g] - 1 : kb);
+                o.b[g] = lds_f64(bb + (unsigned)((g0 + g) * P.ks + 4 * kb) * 64u + bcol);
+            }
+        };
+        auto advance = [&]() {                           // next block of 4 positions along the ring
+            ++blk0;
+            if (G > 1) {
+                if (++sub == 4) {
+                    sub = 0;
+                    if (++slot == P.nslot) slot = 0;
+                }
+            } else {
+                sub += 32;
+                if (sub >= 128) {
+                    sub -= 128;
+                    ++jcur;
+                    if (++slot == P.nslot) slot = 0;
+                }
+            }
+        };
+        // Set tile t up (index arithmetic, barrier waits) and load the operands of its first block into `o`.
+        // Runs underneath the last block of the tile before it.
+        auto setup = [&](int64_t t, Ops& o) {
             const int64_t u = t - t0;
             const int s = (int)(u & 1);
-            const int64_t q = xq_nx - P.tapsper + 1;
-            int n = (int)((x7_nx - xq_nx + P.tapsper + 3) >> 2);
-            nks = n < nks_max ? n : nks_max;
-            const int64_t hi = (xe_nx + 1 - pos_base + (kFtSlotPos - 1)) >> 4;     // slots [0, hi) hold the tile's window
-            if (t + 1 < t1) {
-                xq_nx = __ldg(P.xi0 + (t + 1) * kFmT + 8 * g);
-                x7_nx = __ldg(P.xi0 + (t + 1) * kFmT + 8 * g + 7);
-                xe_nx = __ldg(P.xi0 + (t + 1) * kFmT + kFmT - 1);
+            int64_t ab[G];
+            int last = 0;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int64_t r = xq_nx[g] - P.tapsper + 1 - pos_base;               // >= 0: first window position of the group
+                ab[g] = r >> 2;
+                nb[g] = (int)(((G > 1 ? (r & 3) : 0) + (x7_nx[g] - xq_nx[g]) + P.tapsper + 3) >> 2);
+                nb[g] = nb[g] < (P.ks >> 2) ? nb[g] : (P.ks >> 2);
             }
-            const int64_t rel = q - pos_base + kk;                                   // >= 0
-            const int64_t j0 = rel >> 4;
-            slot_t += (int)(j0 - jslot0);                                            // windows only move forward, a few slots per tile
-            jslot0 = j0;
-            while (slot_t >= P.nslot) slot_t -= P.nslot;
-            slot = slot_t;
-            up = (int)(rel & 15) << 3;
-            bp = bands + s * band_tile + (unsigned)(g * P.ks + kk) * 64u + nn * 8u;
+            const int64_t rlane = xq_nx[0] - P.tapsper + 1 - pos_base + kk;          // (G == 1) my position of block 0
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                ob[g] = (int)(ab[g] - ab[0]);
+                last = last > ob[g] + nb[g] ? last : ob[g] + nb[g];
+            }
+            nbt = last;
+            if (t + 1 < t1) fetch_idx(t + 1);
+            // ring position of the tile's first block, relative to the block loaded last (the end of the tile in
+            // flight): a few blocks back, windows overlap
+            if (G > 1) {
+                const int adv = (int)(ab[0] - blk0);
+                blk0 = ab[0];
+                sub += adv;
+                slot += sub >> 2;                       // (arithmetic shift: floor for negative steps)
+                sub &= 3;
+            } else {
+                const int64_t j_new = rlane >> 4;       // global slot index of my position of block 0
+                slot += (int)(j_new - jcur);
+                jcur = j_new;
+                sub = (int)(rlane & 15) << 3;
+            }
+            while (slot >= P.nslot) slot -= P.nslot;
+            while (slot < 0) slot += P.nslot;
+            bandbase = bands + s * band_tile;
+            // one barrier per tile: the helpers arrive on it once the tile's band is built AND its ring slots
+            // have landed (they watch the `full` barriers, off the compute warps' path)
             const long long c0 = P.dbg ? clock64() : 0;
             mbar_wait(&bar_taps[s], (unsigned)(u >> 1) & 1u);
-            const long long c1 = P.dbg ? clock64() : 0;
-            while (jwait < hi) {
-                mbar_wait(&bar_full[jw_slot], jw_par);
-                ++jwait;
-                if (++jw_slot == P.nslot) { jw_slot = 0; jw_par ^= 1u; }
-            }
-            if (P.dbg) {
-                const long long c2 = clock64();
-                dbg_acc[0] += c1 - c0; dbg_acc[1] += c2 - c1;
-            }
-            const unsigned ap = arow + slot * kFtSlotBytes + ((unsigned)up ^ key);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = lds_f64(ap + i * 1024);
-            b = lds_f64(bp);
+            if (P.dbg) dbg_acc[0] += clock64() - c0;
+            load_ops(o, 0, bandbase, ob, nb);
         };
-        // operands of k-step `ksn` of the tile in flight (the next one along its stream)
-        auto load_next = [&](double (&a)[8], double& b, unsigned bp_t, int ksn) {
-            up += 32;
-            if (up >= 128) {
-                up -= 128;
-                if (++slot == P.nslot) slot = 0;
+        auto mma_block = [&](double (&acc)[F][G][2], const Ops& o, int b, const int (&obx)[G], const int (&nbx)[G]) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                if (G == 1 || (b >= obx[g] && b < obx[g] + nbx[g])) {
+#pragma unroll
+                    for (int i = 0; i < F; ++i) dmma884(acc[i][g][0], acc[i][g][1], o.a[i], o.b[g]);
+                }
             }
-            const unsigned ap = arow + slot * kFtSlotBytes + ((unsigned)up ^ key);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = lds_f64(ap + i * 1024);
-            b = lds_f64(bp_t + ksn * 256);
-        };
-        auto mma8 = [&](double (&acc)[8][2], const double (&a)[8], double b) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dmma884(acc[i][0], acc[i][1], a[i], b);
         };
         // fragments of a finished tile -> staging (the store thread has read the tile before it out of it)
-        auto stage_out = [&](double (&o)[8][2], int64_t u_old) {
+        auto stage_out = [&](double (&o)[F][G][2], int64_t u_old) {
             const long long c0 = P.dbg ? clock64() : 0;
             if (u_old > 0) mbar_wait(&bar_stg_free, (unsigned)(u_old - 1) & 1u);
             if (P.dbg) dbg_acc[2] += clock64() - c0;
             if (!(P.exp & 1)) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) sts_v2f64(srow + i * 1024, o[i][0], o[i][1]);
+                for (int g = 0; g < G; ++g) {
+                    const int gg = g0 + g;
+                    const unsigned sp = srow + (gg >> 1) * 16384 + ((unsigned)(((gg & 1) * 4 + kk) << 4) ^ key);
+#pragma unroll
+                    for (int i = 0; i < F; ++i) sts_v2f64(sp + i * 1024, o[i][g][0], o[i][g][1]);
+                }
             }
             fence_async_smem();
             __syncwarp();
@@ -252,50 +304,59 @@ k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtens
             if (SSQ) {
                 // outputs past n_out have all-zero taps, rows past the last read zeros: exactly 0
 #pragma unroll
-                for (int i = 0; i < 8; ++i) ssq[i] = fma(o[i][0], o[i][0], fma(o[i][1], o[i][1], ssq[i]));
+                for (int i = 0; i < F; ++i)
+#pragma unroll
+                    for (int g = 0; g < G; ++g)
+                        ssq[G * i + g] = fma(o[i][g][0], o[i][g][0], fma(o[i][g][1], o[i][g][1], ssq[G * i + g]));
             }
         };
         // One tile: its DMMAs accumulate into `acc` while the fragments of the tile before it (`old`) drain to
-        // the staging boxes underneath them and, during the last k-step, the next tile is set up and its
+        // the staging boxes underneath them and, during the last block, the next tile is set up and its
         // first operands are fetched: the tensor pipe is never left waiting for a tile boundary.  On entry
-        // set 0 holds the operands of k-step 0; on exit it holds those of the next tile's.
-        auto tile = [&](double (&acc)[8][2], double (&old)[8][2], int64_t t) {
+        // o0 holds the operands of block 0; on exit it holds those of the next tile's.
+        auto tile = [&](double (&acc)[F][G][2], double (&old)[F][G][2], int64_t t) {
             const int64_t u = t - t0;
             const bool more = t + 1 < t1;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.0;
-            const int n = nks;
-            const unsigned bp_t = bp;
-            if (n >= 2) {
-                load_next(a1, b1, bp_t, 1);
-                mma8(acc, a0, b0);
-                if (u > 0) stage_out(old, u - 1);
-                int ks = 1;                                   // set 1 holds k-step ks
-                for (; ks + 2 < n; ks += 2) {
-                    load_next(a0, b0, bp_t, ks + 1);
-                    mma8(acc, a1, b1);
-                    load_next(a1, b1, bp_t, ks + 2);
-                    mma8(acc, a0, b0);
-                }
-                if (n - ks == 2) {
-                    load_next(a0, b0, bp_t, ks + 1);
-                    mma8(acc, a1, b1);
-                    if (more) setup(t + 1, a1, b1);
-                    mma8(acc, a0, b0);
+            for (int i = 0; i < F; ++i)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) a0[i] = a1[i];
-                    b0 = b1;
+                for (int g = 0; g < G; ++g) acc[i][g][0] = acc[i][g][1] = 0.0;
+            // this tile's schedule (setup of the next tile overwrites the shared copies)
+            const int n = nbt;
+            const unsigned bb = bandbase;
+            int obt[G], nbx[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) { obt[g] = ob[g]; nbx[g] = nb[g]; }
+            if (n >= 2) {
+                advance();
+                load_ops(o1, 1, bb, obt, nbx);
+                mma_block(acc, o0, 0, obt, nbx);
+                if (u > 0) stage_out(old, u - 1);
+                int b = 1;                                    // o1 holds block b
+                for (; b + 2 < n; b += 2) {
+                    advance();
+                    load_ops(o0, b + 1, bb, obt, nbx);
+                    mma_block(acc, o1, b, obt, nbx);
+                    advance();
+                    load_ops(o1, b + 2, bb, obt, nbx);
+                    mma_block(acc, o0, b + 1, obt, nbx);
+                }
+                if (n - b == 2) {
+                    advance();
+                    load_ops(o0, b + 1, bb, obt, nbx);
+                    mma_block(acc, o1, b, obt, nbx);
+                    if (more) setup(t + 1, o1);
+                    mma_block(acc, o0, b + 1, obt, nbx);
+                    o0 = o1;
                 } else {
-                    if (more) setup(t + 1, a0, b0);
-                    mma8(acc, a1, b1);
+                    if (more) setup(t + 1, o0);
+                    mma_block(acc, o1, b, obt, nbx);
                 }
             } else {
-                if (more) setup(t + 1, a1, b1);
-                mma8(acc, a0, b0);
+                if (more) setup(t + 1, o1);
+                mma_block(acc, o0, 0, obt, nbx);
                 if (u > 0) stage_out(old, u - 1);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) a0[i] = a1[i];
-                b0 = b1;
+                o0 = o1;
             }
             __syncwarp();
             if (lane == 0) {
@@ -304,8 +365,8 @@ k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtens
             }
         };
 
-        double accA[8][2], accB[8][2];
-        setup(t0, a0, b0);
+        double accA[F][G][2], accB[F][G][2];
+        setup(t0, o0);
         const long long cstart = P.dbg ? clock64() : 0;
         for (int64_t t = t0; t < t1; t += 2) {
             tile(accA, accB, t);
@@ -313,14 +374,16 @@ k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtens
         }
         if (P.dbg && warp == 0 && lane == 0) {
             long long* d = P.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8;
-            d[0] = dbg_acc[0]; d[1] = dbg_acc[1]; d[2] = dbg_acc[2]; d[3] = clock64() - cstart;
+            d[0] = dbg_acc[0]; d[1] = 0; d[2] = dbg_acc[2]; d[3] = clock64() - cstart;
         }
         if ((t1 - t0) & 1) stage_out(accA, t1 - t0 - 1);
         else stage_out(accB, t1 - t0 - 1);
         if (SSQ) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                double v = ssq[i];
+            for (int i = 0; i < F; ++i) {
+                double v = 0.0;
+#pragma unroll
+                for (int g = 0; g < G; ++g) v += ssq[G * i + g];
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
                 const int64_t row = (int64_t)row0 + rloc + 8 * i;
@@ -329,19 +392,26 @@ k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtens
         }
     } else if (warp < kFtNCW + kFtNAW) {
         // ---------------- tap bands: helper warp g merges the taps of output group g — on the tensor pipe ----------------
-        // h[t][n] = pfb[phi_n][t] + alpha_n * dpfb[phi_n][t] for the group's 8 outputs n is itself a small matrix
-        // product: C (8 taps x 8 outputs, preloaded with the pfb values) += A (8 taps x 8: dpfb values) * B
-        // (diag(alpha)), two DMMA.8x8x4 per 8 taps.  Scalar FP64 instructions of a helper warp queue behind the
-        // DMMAs of the compute warps on the same sub-partition (measured here: ~200 cycles per DFMA, 4500 cycles
-        // per tile for one FMA per merged tap); DMMAs of another warp simply interleave, at 5.5 % more
-        // tensor work.  Operands are table look-ups and selects: no FP64 ALU instruction in this branch.
+        // h[k][n] = pfb[phi_n][k - s_n] + alpha_n * dpfb[phi_n][k - s_n] for band rows k and the group's 8 outputs n
+        // (s_n = where output n's taps start in the band, zero outside) is itself a small matrix product:
+        // C (8 rows x 8 outputs, preloaded with the pfb values) += A (8 rows x 8: dpfb values) * B (diag(alpha)),
+        // two DMMA.8x8x4 per 8 band rows.  Scalar FP64 instructions of a helper warp queue behind the DMMAs of
+        // the compute warp on the same sub-partition (measured here: ~200 cycles per DFMA, 4500 cycles per tile
+        // for one FMA per merged tap); DMMAs of another warp simply interleave, at 6 % more tensor work.
+        // Operands are table look-ups and selects: no FP64 ALU instruction in this branch.  Whole band rows are
+        // written (zeros included) as 16-byte pairs.  Band row 0 sits at the group's first window position
+        // rounded down to a multiple of 4 ring positions, so that the compute warps can share A blocks.
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kFtRegsHelper));
         const int grp = warp - kFtNCW;
         const int kk = lane & 3, rr = lane >> 2;
         const unsigned pf_tab = tabs, dpf_tab = tabs + 8u * P.tab_doubles;
         const bool has_d = P.dpfb != nullptr;
-        const int nblk = (P.tapsper + 7) >> 3;            // 8-tap row blocks
+        const int nblk = P.ks >> 3;                        // 8-row band blocks (ks is a multiple of 8 here)
         long long hdbg[2] = {0, 0};
+        int64_t jwait = 0;                              // ring slots [0, jwait) have been seen to land
+        int jw_slot = 0;
+        unsigned jw_par = 0;
+        int64_t xe_nx = __ldg(P.xi0 + t0 * kFmT + kFmT - 1);
         // lane l < 8 carries column l of the group (others mirror it)
         int64_t xi_nx = __ldg(P.xi0 + t0 * kFmT + 8 * grp + (lane & 7));
         int po_nx = __ldg(P.poff + t0 * kFmT + 8 * grp + (lane & 7));
@@ -354,49 +424,50 @@ k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtens
             const bool live = m < P.n_out;
             const int po = po_nx;
             const double al = live ? al_nx : 0.0;
+            const int64_t hi = (xe_nx + 1 - pos_base + (kFtSlotPos - 1)) >> 4;     // slots [0, hi) hold the tile's window
             if (t + 1 < t1) {
                 xi_nx = __ldg(P.xi0 + m + kFmT);
                 po_nx = __ldg(P.poff + m + kFmT);
                 al_nx = __ldg(P.alpha + m + kFmT);
+                xe_nx = __ldg(P.xi0 + (t + 1) * kFmT + kFmT - 1);
             }
             const int64_t xg = __shfl_sync(0xffffffffu, xi, 0);
-            const int sh = (int)(xi - xg);                                       // band rows [sh, sh + tapsper) hold column (lane & 7)'s taps
+            const int og = P.aligned ? (int)((xg - P.tapsper + 1 - pos_base) & 3) : 0;   // the group's window start inside its first aligned block
+            // band rows [st, st + tapsper) hold column (lane & 7)'s taps; a dead column (past n_out) holds none
+            const int st = live ? (int)(xi - xg) + og : (1 << 20);
             // what my fragment elements need: C columns 2kk, 2kk+1; A columns kk, 4+kk; B column rr
-            const int sh_c0 = __shfl_sync(0xffffffffu, sh, 2 * kk), sh_c1 = __shfl_sync(0xffffffffu, sh, 2 * kk + 1);
+            const int st_c0 = __shfl_sync(0xffffffffu, st, 2 * kk), st_c1 = __shfl_sync(0xffffffffu, st, 2 * kk + 1);
             const int po_c0 = __shfl_sync(0xffffffffu, po, 2 * kk), po_c1 = __shfl_sync(0xffffffffu, po, 2 * kk + 1);
+            const int st_a0 = __shfl_sync(0xffffffffu, st, kk), st_a1 = __shfl_sync(0xffffffffu, st, 4 + kk);
             const int po_a0 = __shfl_sync(0xffffffffu, po, kk), po_a1 = __shfl_sync(0xffffffffu, po, 4 + kk);
-            const unsigned lv = __ballot_sync(0xffffffffu, live);
-            const bool lv_c0 = (lv >> (2 * kk)) & 1u, lv_c1 = (lv >> (2 * kk + 1)) & 1u;
-            const bool lv_a0 = (lv >> kk) & 1u, lv_a1 = (lv >> (4 + kk)) & 1u;
             const double al_b = __shfl_sync(0xffffffffu, al, rr);
             const double b0 = (kk == rr) ? al_b : 0.0, b1 = (4 + kk == rr) ? al_b : 0.0;
             const unsigned band = bands + s * band_tile + (unsigned)(grp * P.ks) * 64u;
-            auto cell = [&](int k, int n) { return band + 8u * (unsigned)(k * 8 + (n ^ (((k >> 1) & 1) << 2))); };
             // tile t-2 must be finished: its band buffer is about to be overwritten
             const long long c0 = P.dbg ? clock64() : 0;
             if (u >= 2) mbar_wait(&bar_done[(u - 2) & 3], (unsigned)((u - 2) >> 2) & 1u);
             const long long c1 = P.dbg ? clock64() : 0;
             hdbg[0] += c1 - c0;
-            // rows outside a column's taps are zero (the buffer still holds tile t-2's band): lane = (column, row mod 4)
-            {
-                const int n = lane & 7, part = lane >> 3;
-                const int top = live ? sh : 0, bot = live ? sh + P.tapsper : 0;
-                for (int k = part; k < P.ks; k += 4)
-                    if (k < top || k >= bot) sts_f64(cell(k, n), 0.0);
-            }
             for (int b = 0; b < nblk; ++b) {
-                const int tt = 8 * b + rr;                                       // my tap row
-                const bool in = tt < P.tapsper;
-                double cv0 = (in && lv_c0) ? lds_f64(pf_tab + 8u * (unsigned)(po_c0 + tt)) : 0.0;
-                double cv1 = (in && lv_c1) ? lds_f64(pf_tab + 8u * (unsigned)(po_c1 + tt)) : 0.0;
+                const int k = 8 * b + rr;                                        // my band row
+                const unsigned tc0 = (unsigned)(k - st_c0), tc1 = (unsigned)(k - st_c1);   // tap indices (unsigned: one range test)
+                const unsigned ta0 = (unsigned)(k - st_a0), ta1 = (unsigned)(k - st_a1);
+                double cv0 = tc0 < (unsigned)P.tapsper ? lds_f64(pf_tab + 8u * ((unsigned)po_c0 + tc0)) : 0.0;
+                double cv1 = tc1 < (unsigned)P.tapsper ? lds_f64(pf_tab + 8u * ((unsigned)po_c1 + tc1)) : 0.0;
                 if (has_d) {
-                    const double a0 = (in && lv_a0) ? lds_f64(dpf_tab + 8u * (unsigned)(po_a0 + tt)) : 0.0;
-                    const double a1 = (in && lv_a1) ? lds_f64(dpf_tab + 8u * (unsigned)(po_a1 + tt)) : 0.0;
+                    const double a0 = ta0 < (unsigned)P.tapsper ? lds_f64(dpf_tab + 8u * ((unsigned)po_a0 + ta0)) : 0.0;
+                    const double a1 = ta1 < (unsigned)P.tapsper ? lds_f64(dpf_tab + 8u * ((unsigned)po_a1 + ta1)) : 0.0;
                     dmma884(cv0, cv1, a0, b0);
                     dmma884(cv0, cv1, a1, b1);
                 }
-                if (in && lv_c0) sts_f64(cell(sh_c0 + tt, 2 * kk), cv0);
-                if (in && lv_c1) sts_f64(cell(sh_c1 + tt, 2 * kk + 1), cv1);
+                // columns 2kk, 2kk+1 stay adjacent under the XOR on bit 2 of the column index
+                sts_v2f64(band + 8u * (unsigned)(k * 8 + ((2 * kk) ^ (((k >> 1) & 1) << 2))), cv0, cv1);
+            }
+            // ... and the tile's window has landed in the ring
+            while (jwait < hi) {
+                mbar_wait(&bar_full[jw_slot], jw_par);
+                ++jwait;
+                if (++jw_slot == P.nslot) { jw_slot = 0; jw_par ^= 1u; }
             }
             mbar_arrive(&bar_taps[s]);
             if (P.dbg) hdbg[1] += clock64() - c1;

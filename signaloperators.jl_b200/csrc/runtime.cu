@@ -1082,7 +1082,8 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                 };
                 char *bin = nullptr, *bout = nullptr;
                 int64_t sin_ = 0, sout = 0;
-                const int ks = (int)round_up(s.fir.dpad + g.taps_per_phase, 4);
+                // a group's band starts at its first window position rounded down to a multiple of 4 ring positions
+                const int ks = (int)round_up(s.fir.dpad + g.taps_per_phase + 3, 8);
                 const int win_slots = (s.fir.pmax32 + 14) / 16 + 1;          // worst alignment of a tile's window
                 int nslot = kFtMaxSlots;
                 const bool has_d = P.dpfb != nullptr;
@@ -1101,6 +1102,11 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                     T.tab_doubles = (int)tabd_;
                     T.gain = s.fir.epi_scale;
                     if (const char* e = getenv("SIGOPS_FIR_EXP")) T.exp = atoi(e);
+                    // output groups per compute warp: measured on config 3, sharing A blocks between groups (2: 1.79 ms,
+                    // 4: 2.20 ms) loses to one group per warp (1.43 ms) — the loop is bound by issue order, not by
+                    // shared-memory bandwidth — so 1 is the default and the others stay as tuning knobs
+                    const int gsel = getenv("SIGOPS_FIR_GROUPS") ? atoi(getenv("SIGOPS_FIR_GROUPS")) : 1;
+                    T.aligned = gsel == 1 ? 0 : 1;
                     const int64_t groups = (rows + kFtRows - 1) / kFtRows;
                     // segments along the time axis: whole waves of one block per SM; a segment pays about
                     // three tiles of start-up (first window, pipeline fill)
@@ -1133,8 +1139,8 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                             CUDA_OK(cudaMemset(dbg, 0, nb * 8 * sizeof(long long)));
                             FirTmParams D = T;
                             D.dbg = dbg;
-                            ensure_dyn_smem(k_fir_tmap<false>, smem);
-                            k_fir_tmap<false><<<tgrid, kFtThreads, smem, stream>>>(D, *(const CUtensorMap*)&mi, *(const CUtensorMap*)&mo);
+                            ensure_dyn_smem(k_fir_tmap<false, 1>, smem);
+                            k_fir_tmap<false, 1><<<tgrid, kFtThreads, smem, stream>>>(D, *(const CUtensorMap*)&mi, *(const CUtensorMap*)&mo);
                             CUDA_OK(cudaStreamSynchronize(stream));
                             std::vector<long long> h(nb * 8);
                             CUDA_OK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -1149,13 +1155,16 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                         add(KIND_FIR, [=](cudaStream_t st) {
                             const CUtensorMap& a = *(const CUtensorMap*)&mi;
                             const CUtensorMap& b = *(const CUtensorMap*)&mo;
-                            if (ssq) {
-                                ensure_dyn_smem(k_fir_tmap<true>, smem);
-                                k_fir_tmap<true><<<tgrid, kFtThreads, smem, st>>>(T, a, b);
-                            } else {
-                                ensure_dyn_smem(k_fir_tmap<false>, smem);
-                                k_fir_tmap<false><<<tgrid, kFtThreads, smem, st>>>(T, a, b);
-                            }
+#define SIGOPS_FIR_TM_CASE(SSQ_, G_)                                        \
+    {                                                                        \
+        ensure_dyn_smem(k_fir_tmap<SSQ_, G_>, smem);                         \
+        k_fir_tmap<SSQ_, G_><<<tgrid, kFtThreads, smem, st>>>(T, a, b);      \
+    }
+                            if (ssq) SIGOPS_FIR_TM_CASE(true, 1)
+                            else if (gsel == 2) SIGOPS_FIR_TM_CASE(false, 2)
+                            else if (gsel == 4) SIGOPS_FIR_TM_CASE(false, 4)
+                            else SIGOPS_FIR_TM_CASE(false, 1)
+#undef SIGOPS_FIR_TM_CASE
                         });
                         continue;
                     }

@@ -1,2 +1,3 @@
-for e in 0 1 3 4 8 12 7; do echo "EXP=$e"; SIGOPS_FIR_EXP=$e SIGOPS_FIR_DBG=1 timeout -k 10 120 python tools/profile_step.py cfg3 3 2>&1 | tail -2; done
-for ns in 7 8; do echo "NSLOT=$ns"; SIGOPS_FIR_NSLOT=$ns SIGOPS_FIR_DBG=1 timeout -k 10 120 python tools/profile_step.py cfg3 3 2>&1 | tail -2; done
+for g in 1 2; do echo "GROUPS=$g"; SIGOPS_FIR_GROUPS=$g timeout -k 10 120 python tools/profile_step.py cfg3 5 2>&1 | tail -1; done
+SIGOPS_FIR_DBG=1 timeout -k 10 120 python tools/profile_step.py cfg3 5 2>&1 | tail -2
+timeout -k 10 200 python tools/profile_step.py cfg3 5 1024 2>&1 | tail -1
