@@ -74,7 +74,8 @@ struct FirTmParams {
     int aligned;            // 1: band row 0 = the group's first window position rounded down to a multiple of 4 ring
                             //    positions (compute warps share A blocks between groups, G > 1); 0: exactly that position
     long long* dbg;         // optional [blocks][8] cycle counters (tuning aid, SIGOPS_FIR_DBG=1), or nullptr
-    int exp;                // tuning experiments (SIGOPS_FIR_EXP bit mask; wrong results): 1 no staging stores, 2 no tensor stores
+    int exp;                // tuning experiments (SIGOPS_FIR_EXP bit mask; wrong results): 1 no staging stores, 2 no tensor
+                            // stores, 4 no tap-band building
 };
 
 inline size_t fir_tm_smem_bytes(int nslot, int ks, int tab_doubles, bool has_dpfb) {
@@ -448,7 +449,7 @@ k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtens
             if (u >= 2) mbar_wait(&bar_done[(u - 2) & 3], (unsigned)((u - 2) >> 2) & 1u);
             const long long c1 = P.dbg ? clock64() : 0;
             hdbg[0] += c1 - c0;
-            for (int b = 0; b < nblk; ++b) {
+            for (int b = 0; b < ((P.exp & 4) ? 0 : nblk); ++b) {
                 const int k = 8 * b + rr;                                        // my band row
                 const unsigned tc0 = (unsigned)(k - st_c0), tc1 = (unsigned)(k - st_c1);   // tap indices (unsigned: one range test)
                 const unsigned ta0 = (unsigned)(k - st_a0), ta1 = (unsigned)(k - st_a1);

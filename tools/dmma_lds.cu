@@ -2,6 +2,7 @@
 // fresh shared-memory loads (the k_fir_tmap inner loop), for 1..4 warps per sub-partition and NL loads per
 // 8 DMMAs?  build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/dmma_lds tools/dmma_lds.cu
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 __device__ __forceinline__ double lds(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
@@ -56,9 +57,31 @@ void run(int sms, double* out) {
     }
 }
 
-int main() {
+// the same loop held for `seconds`: the sustained rate under the board's power cap (clocks drop)
+void sustained(int sms, double* out, double seconds) {
+    const int iters = 20000, threads = 256;
+    cudaFuncSetAttribute(k<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const double dm = (double)sms * (threads / 32) * iters * 8;
+    float ms1;
+    cudaEventRecord(e0); k<8><<<sms, threads, 160 * 1024>>>(out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms1, e0, e1);
+    const int n = (int)(seconds * 1e3 / ms1) + 1;
+    const int tail = n / 4 > 0 ? n / 4 : 1;
+    for (int i = 0; i < n - tail; ++i) k<8><<<sms, threads, 160 * 1024>>>(out, iters);
+    cudaEventRecord(e0);
+    for (int i = 0; i < tail; ++i) k<8><<<sms, threads, 160 * 1024>>>(out, iters);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    printf("sustained %.1f s, 2 warps/SMSP, 9 loads per 8 DMMAs: %.2f T FMA/s over the last quarter (burst launch: %.2f)\n", seconds,
+           dm * tail * 256 / (ms * 1e-3) / 1e12, dm * 256 / (ms1 * 1e-3) / 1e12);
+}
+
+int main(int argc, char** argv) {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     double* out; cudaMalloc(&out, sizeof(double) * p.multiProcessorCount * 1024);
+    if (argc > 1) { sustained(p.multiProcessorCount, out, atof(argv[1])); return 0; }
     run<0>(p.multiProcessorCount, out);
     run<2>(p.multiProcessorCount, out);
     run<4>(p.multiProcessorCount, out);
