@@ -93,9 +93,20 @@ void sigops_plan_destroy(sigops_plan* plan);
 int sigops_plan_run(sigops_plan* plan, int64_t ninst,
                     const sigops_buffer* in, sigops_buffer* out, sigops_stats* stats);
 
+/* Page-locked host memory for sample buffers.  `sigops_plan_run` accepts ANY host pointer: page-locked
+ * memory (from here, cudaHostAlloc or cudaHostRegister) is read and written by the DMA engines directly;
+ * pageable memory (a plain Julia `Array`, malloc) is staged through the library's own pinned ring by a few
+ * copy threads, which costs about a third of the end-to-end throughput.  The glue allocates the RESULT of
+ * `sink(x, GPUSink())` here (the reference allocates it itself at src/sink.jl:115-121, so there is no
+ * caller array to honour) and releases it from the array's finalizer. */
+int sigops_host_alloc(size_t bytes, void** out);
+int sigops_host_free(void* ptr);
+
 /* Same, with every buffer already resident on ctx device `dev_index`.  Work is
  * enqueued on `cuda_stream` (a cudaStream_t; NULL = the library's own stream)
- * and the call returns without synchronising when a stream is given. */
+ * and the call returns without synchronising when a stream is given.  All calls on one ctx device share
+ * one workspace; the library orders them itself (an event behind every call, waited for by the next call
+ * on a different stream), so asynchronous calls on several streams are safe but do not overlap. */
 int sigops_plan_run_device(sigops_plan* plan, int dev_index, int64_t ninst,
                            const sigops_buffer* in, sigops_buffer* out,
                            void* cuda_stream, sigops_stats* stats);

@@ -78,14 +78,30 @@ struct Arena {
     }
 };
 
+constexpr int kTableRing = 4;
+
 struct Slot {
     cudaStream_t stream = nullptr;
     Arena arena;
-    void* pinned = nullptr;      // staging for the BufRef table
-    size_t pinned_cap = 0;
+    // pinned staging for the BufRef table: a small ring, each entry guarded by the event recorded behind
+    // its upload, so that a new table never waits for the stream to drain
+    void* pinned[kTableRing] = {};
+    size_t pinned_cap[kTableRing] = {};
+    cudaEvent_t pinned_ev[kTableRing] = {};
+    int pinned_next = 0;
     std::vector<char> last_table; // contents last uploaded (skip identical re-uploads)
     void* last_table_dev = nullptr;
     cudaEvent_t ev[6] = {};
+    // everything a call enqueues on this slot ends with this event; the next user of the slot (possibly on
+    // another stream) waits for it before touching the arena, the table or the IIR state
+    cudaEvent_t busy = nullptr;
+    cudaStream_t busy_stream = nullptr;
+    bool busy_valid = false;
+    // the prepared launches of a wave captured as a CUDA graph (replayed when the same plan runs on the same
+    // buffers again and profiling is off)
+    cudaGraphExec_t graph = nullptr;
+    cudaStream_t graph_stream = nullptr;
+    int replays = 0;
     // per-launch timing (sigops_ctx_set_profiling): (start, stop, kernel kind)
     // prepared launches of the last wave (replayed when the same plan runs on the same buffers)
     struct Prepared {
@@ -126,10 +142,36 @@ struct ProfScope {          // brackets one kernel launch with events when profi
     }
 };
 
+constexpr int kHostSlots = 3;       // staging buffers of the host-buffer pipeline (H2D | kernels | D2H in flight at once)
+
+// Pinned staging ring for caller arrays that are NOT page-locked (a Julia `Array`, a numpy array):
+// worker threads copy user memory <-> pinned chunks, the DMA engines move pinned <-> device.
+struct PinnedStage {
+    char* base = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (base) cudaFreeHost(base);
+        base = nullptr;
+        cap = 0;
+        CUDA_OK(cudaHostAlloc((void**)&base, bytes, cudaHostAllocDefault));
+        cap = bytes;
+    }
+    void release() {
+        if (base) cudaFreeHost(base);
+        base = nullptr;
+        cap = 0;
+    }
+};
+
 struct Device {
     int ordinal = 0;
     int sm_count = 148;
-    Slot slots[2];
+    Slot slots[kHostSlots];
+    cudaStream_t s_in = nullptr, s_out = nullptr;          // copy streams of the host-buffer pipeline
+    cudaEvent_t ev_in[kHostSlots] = {}, ev_k[kHostSlots] = {}, ev_out[kHostSlots] = {};
+    cudaEvent_t ev_t[kHostSlots][4] = {};                    // timing: H2D start/stop, D2H start/stop
+    PinnedStage stage_in[kHostSlots], stage_out[kHostSlots];
 };
 
 // ---- per-stage derived data ---------------------------------------------------
@@ -177,6 +219,7 @@ struct PlanDev {               // device-resident constants of a plan
     std::vector<double*> phi;
     std::vector<int32_t*> poff;
     std::vector<double*> alpha;
+    std::unordered_map<uint64_t, double*> carry;   // (stage, chunk length) -> device copy of the L-step transition matrix
 };
 
 }  // namespace
@@ -661,6 +704,8 @@ void free_plan_dev(sigops_plan& p) {
         for (auto q : d.phi) cudaFree(q);
         for (auto q : d.poff) cudaFree(q);
         for (auto q : d.alpha) cudaFree(q);
+        for (auto& kv : d.carry) cudaFree(kv.second);
+        d.carry.clear();
         d.ready = false;
     }
 }
@@ -786,12 +831,6 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
 
     // -- BufRef table (instance-major)
     const size_t table_bytes = (size_t)ninst * nbuf * sizeof(BufRef);
-    if (slot.pinned_cap < table_bytes) {
-        if (slot.pinned) cudaFreeHost(slot.pinned);
-        slot.pinned = nullptr;
-        CUDA_OK(cudaMallocHost(&slot.pinned, table_bytes));
-        slot.pinned_cap = table_bytes;
-    }
     std::vector<char> table(table_bytes);
     BufRef* refs = (BufRef*)table.data();
     for (int64_t i = 0; i < ninst; ++i) {
@@ -816,10 +855,21 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
     }
     bool table_changed = false;
     if (slot.last_table_dev != (void*)d_refs || slot.last_table != table) {
-        // the pinned staging buffer may still be in flight from the previous wave of this slot
-        CUDA_OK(cudaStreamSynchronize(stream));
-        memcpy(slot.pinned, table.data(), table_bytes);
-        CUDA_OK(cudaMemcpyAsync(d_refs, slot.pinned, table_bytes, cudaMemcpyHostToDevice, stream));
+        // next entry of the pinned ring; its previous upload (kTableRing waves ago) has long completed
+        const int r = slot.pinned_next;
+        slot.pinned_next = (r + 1) % kTableRing;
+        if (!slot.pinned_ev[r]) CUDA_OK(cudaEventCreateWithFlags(&slot.pinned_ev[r], cudaEventDisableTiming));
+        else CUDA_OK(cudaEventSynchronize(slot.pinned_ev[r]));
+        if (slot.pinned_cap[r] < table_bytes) {
+            if (slot.pinned[r]) cudaFreeHost(slot.pinned[r]);
+            slot.pinned[r] = nullptr;
+            slot.pinned_cap[r] = 0;
+            CUDA_OK(cudaMallocHost(&slot.pinned[r], table_bytes));
+            slot.pinned_cap[r] = table_bytes;
+        }
+        memcpy(slot.pinned[r], table.data(), table_bytes);
+        CUDA_OK(cudaMemcpyAsync(d_refs, slot.pinned[r], table_bytes, cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaEventRecord(slot.pinned_ev[r], stream));
         slot.last_table.swap(table);
         slot.last_table_dev = d_refs;
         table_changed = true;
@@ -834,7 +884,41 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
         }
         return (int64_t)slot.cache_launches.size();
     };
-    if (!table_changed && slot.cache_plan == p.uid && slot.cache_ninst == ninst) return replay();
+    auto drop_graph = [&]() {
+        if (slot.graph) cudaGraphExecDestroy(slot.graph);
+        slot.graph = nullptr;
+        slot.replays = 0;
+    };
+    if (!table_changed && slot.cache_plan == p.uid && slot.cache_ninst == ninst) {
+        // Same plan on the same buffers again: from the second replay on, the scalar reset and every launch of
+        // the wave go out as ONE cudaGraphLaunch (plans of several small stages are launch-latency bound).
+        static const bool no_graph = getenv("SIGOPS_NO_GRAPH") != nullptr;
+        const bool want_graph = !no_graph && !p.ctx->profiling && slot.cache_launches.size() >= 2;
+        if (want_graph && slot.graph && slot.graph_stream == stream) {
+            CUDA_OK(cudaGraphLaunch(slot.graph, stream));
+            return (int64_t)slot.cache_launches.size();
+        }
+        if (want_graph && ++slot.replays >= 2) {
+            drop_graph();
+            cudaGraph_t gr = nullptr;
+            if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                cudaMemsetAsync(scalars, 0, (size_t)ninst * nscal * sizeof(double), stream);
+                for (auto& L : slot.cache_launches) L.fn(stream);
+                const cudaError_t ce = cudaStreamEndCapture(stream, &gr);
+                if (ce == cudaSuccess && gr && cudaGraphInstantiate(&slot.graph, gr, 0) == cudaSuccess) slot.graph_stream = stream;
+                else slot.graph = nullptr;
+                if (gr) cudaGraphDestroy(gr);
+            }
+            cudaGetLastError();
+            if (slot.graph) {
+                // (the eager memset issued above for this run is harmless: the graph repeats it)
+                CUDA_OK(cudaGraphLaunch(slot.graph, stream));
+                return (int64_t)slot.cache_launches.size();
+            }
+        }
+        return replay();
+    }
+    drop_graph();
     slot.cache_launches.clear();
     slot.cache_plan = 0;
     auto add = [&](int kind, std::function<void(cudaStream_t)> fn) { slot.cache_launches.push_back({kind, std::move(fn)}); };
@@ -1023,10 +1107,14 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                     double cc[kIirMaxSections][5];
                     for (int j = 0; j < s.iir.M; ++j)
                         for (int k = 0; k < 5; ++k) cc[j][k] = P.coef[j][k];
-                    std::vector<double> AL = transition_matrix(cc, s.iir.M, c.L);
-                    double* dAL = (double*)slot.arena.take(AL.size() * sizeof(double));
-                    CUDA_OK(cudaMemcpyAsync(dAL, AL.data(), AL.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
-                    CUDA_OK(cudaStreamSynchronize(stream));   // AL is a host temporary
+                    // L-step transition matrix: computed and uploaded once per (stage, chunk length) and device
+                    const uint64_t akey = ((uint64_t)si << 40) ^ (uint64_t)c.L;
+                    double*& dAL = pd.carry[akey];
+                    if (!dAL) {
+                        std::vector<double> AL = transition_matrix(cc, s.iir.M, c.L);
+                        CUDA_OK(cudaMalloc(&dAL, AL.size() * sizeof(double)));
+                        CUDA_OK(cudaMemcpy(dAL, AL.data(), AL.size() * sizeof(double), cudaMemcpyHostToDevice));
+                    }
                     C.AL = dAL;
                     const unsigned cblocks = (unsigned)((rows + 3) / 4);        // one warp per row
                     add(KIND_IIR_CARRY, [=](cudaStream_t st) { k_iir_carry<<<cblocks, 128, 0, st>>>(C); });
@@ -1354,10 +1442,12 @@ int64_t run_device_resident(sigops_plan& p, int di, int64_t ninst, const sigops_
 }
 
 // Copy buffer `b` of `w` consecutive instances between host and device staging.  A buffer whose
-// rows are dense (ld == nframes on both sides) is one contiguous block; blocks of consecutive
-// instances that are adjacent on both sides are merged, so a batch held in one big host array
-// moves with a single cudaMemcpyAsync per buffer slot instead of one 2-D copy per instance.
-int64_t copy_runs(const sigops_buffer* host, const sigops_buffer* dev, int64_t w, uint32_t nb, bool to_device, cudaStream_t st) {
+// rows are dense (ld == nframes on both sides) is one contiguous block.  `merge`: blocks of consecutive
+// instances that are adjacent on both sides go as ONE cudaMemcpyAsync — only valid when the host side
+// is a single allocation (the library's pinned ring); adjacent caller arrays may be separate page-locked
+// allocations, which one copy must not span.
+int64_t copy_runs(const sigops_buffer* host, const sigops_buffer* dev, int64_t w, uint32_t nb, bool to_device, cudaStream_t st,
+                  bool merge) {
     int64_t total = 0;
     for (uint32_t b = 0; b < nb; ++b) {
         int64_t i = 0;
@@ -1376,7 +1466,7 @@ int64_t copy_runs(const sigops_buffer* host, const sigops_buffer* dev, int64_t w
             }
             const size_t bytes = (size_t)hb.nframes * hb.nchannels * es;
             int64_t j = i + 1;
-            while (j < w && (char*)host[j * nb + b].ptr == (char*)hb.ptr + (j - i) * bytes &&
+            while (merge && j < w && (char*)host[j * nb + b].ptr == (char*)hb.ptr + (j - i) * bytes &&
                    (char*)dev[j * nb + b].ptr == (char*)db.ptr + (j - i) * bytes)
                 ++j;
             if (to_device) CUDA_OK(cudaMemcpyAsync(db.ptr, hb.ptr, bytes * (j - i), cudaMemcpyHostToDevice, st));
@@ -1388,66 +1478,138 @@ int64_t copy_runs(const sigops_buffer* host, const sigops_buffer* dev, int64_t w
     return total;
 }
 
-// ---- host-buffer run: H2D -> stages -> D2H, two pipeline slots per device ----------
+// ---- host-buffer run: H2D | stages | D2H on three streams, three staging buffers per device ----------
 
 struct HostRunResult {
     int64_t launches = 0, h2d = 0, d2h = 0;
     double gpu_ms = 0, h2d_ms = 0, d2h_ms = 0;
+    int staged_waves = 0;
     int code = 0;
     std::string msg;
 };
 
+// Is this caller pointer page-locked (cudaHostAlloc / cudaHostRegister / sigops_host_alloc)?  Anything else is
+// pageable memory, which the DMA engines cannot read directly: cudaMemcpyAsync would fall back to a staged,
+// synchronous copy (measured on the B200 box: 11 GB/s H2D, 22 GB/s D2H instead of 55/57).
+bool is_pinned(const void* ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// memcpy of `n` (dst, src, bytes) pieces spread over a few threads (host DRAM: ~15 GB/s per thread, ~50 with 8)
+struct CopyPiece { char* dst; const char* src; size_t bytes; };
+void parallel_copy(const std::vector<CopyPiece>& pieces, int nthreads) {
+    size_t total = 0;
+    for (auto& c : pieces) total += c.bytes;
+    if (total == 0) return;
+    nthreads = (int)std::max<size_t>(1, std::min<size_t>(nthreads, total >> 22));      // >= 4 MB per thread
+    if (nthreads == 1) {
+        for (auto& c : pieces) memcpy(c.dst, c.src, c.bytes);
+        return;
+    }
+    const size_t share = (total + nthreads - 1) / nthreads;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) {
+        th.emplace_back([&, t] {
+            size_t lo = share * t, hi = std::min(total, lo + share), pos = 0;       // my byte range of the concatenation
+            for (auto& c : pieces) {
+                const size_t a = std::max(lo, pos), b = std::min(hi, pos + c.bytes);
+                if (a < b) memcpy(c.dst + (a - pos), c.src + (a - pos), b - a);
+                pos += c.bytes;
+                if (pos >= hi) break;
+            }
+        });
+    }
+    for (auto& t : th) t.join();
+}
+
+int copy_threads(int ndev) {
+    if (const char* e = getenv("SIGOPS_COPY_THREADS")) return std::max(1, atoi(e));
+    const int hw = (int)std::thread::hardware_concurrency();
+    return std::max(1, std::min(8, (hw > 0 ? hw : 8) / std::max(1, ndev)));
+}
+
 void run_host_on_device(sigops_plan& p, int di, int64_t i_begin, int64_t i_end, const sigops_buffer* in,
                         sigops_buffer* out, HostRunResult& res) {
+    Device& dev = p.ctx->devs[di];
     try {
-        Device& dev = p.ctx->devs[di];
         CUDA_OK(cudaSetDevice(dev.ordinal));
         ensure_plan_dev(p, di);
         const int64_t ninst = i_end - i_begin;
         if (ninst <= 0) return;
         const uint32_t nin = p.h.n_inputs, nout = p.h.n_outputs;
-        // bytes of device staging one instance needs
-        size_t io_bytes = 0;
+        // bytes of device staging one instance needs, and of host data it moves
+        size_t io_bytes = 0, in_host = 0, out_host = 0;
         for (uint32_t b = 0; b < nin + nout; ++b) {
             const sigops_bufdesc& bd = b < nin ? p.bufs[b] : p.bufs[p.h.n_temps + b];
             io_bytes += (size_t)round_up(round_up(std::max<int64_t>(bd.nframes, 1), 16) * bd.nchannels * (int64_t)elem_size(bd.dtype), 256);
+            (b < nin ? in_host : out_host) += (size_t)bd.nframes * bd.nchannels * elem_size(bd.dtype);
         }
-        const size_t budget = p.ctx->ws_budget / 2;
+        // page-locked caller memory is copied from / to directly; anything else goes through the pinned ring
+        bool pinned_in = true, pinned_out = true;
+        for (int64_t i : {i_begin, i_end - 1}) {
+            for (uint32_t b = 0; b < nin; ++b)
+                if (in[i * nin + b].nframes > 0 && !is_pinned(in[i * nin + b].ptr)) pinned_in = false;
+            for (uint32_t b = 0; b < nout; ++b)
+                if (out[i * nout + b].nframes > 0 && !is_pinned(out[i * nout + b].ptr)) pinned_out = false;
+        }
+        if (getenv("SIGOPS_FORCE_STAGING")) pinned_in = pinned_out = false;
+        const size_t budget = p.ctx->ws_budget / kHostSlots;
         int64_t wave = ninst;
         auto need_for = [&](int64_t w) { return wave_workspace_bytes(p, w, dev.sm_count) + io_bytes * w + (size_t)w * (nin + nout) * sizeof(sigops_buffer); };
-        // several waves when the batch allows it, so H2D of wave k+1 and D2H of wave k-1 overlap
-        // the kernels of wave k (the first H2D and last D2H are exposed: 1/nwaves of the copy time)
+        // several waves when the batch allows it, so that H2D of wave k+1, the kernels of wave k and D2H of wave
+        // k-1 overlap (the first H2D and the last D2H are exposed: 1/nwaves of the copy time)
         int nwaves = 16;
         if (const char* e = getenv("SIGOPS_HOST_WAVES")) nwaves = std::max(1, atoi(e));
         if (ninst >= 2 * nwaves) wave = (ninst + nwaves - 1) / nwaves;
         while (wave > 1 && need_for(wave) > budget) wave = (wave + 1) / 2;
-        for (int s = 0; s < 2; ++s) {
+        // pageable callers: bound the pinned ring (page-locking costs ~0.6 s per GB, once per context)
+        const size_t stage_cap = size_t(512) << 20;
+        if (!pinned_in) while (wave > 1 && in_host * wave > stage_cap) wave = (wave + 1) / 2;
+        if (!pinned_out) while (wave > 1 && out_host * wave > stage_cap) wave = (wave + 1) / 2;
+        const int nthreads = copy_threads((int)p.ctx->devs.size());
+        for (int s = 0; s < kHostSlots; ++s) {
             Slot& slot = dev.slots[s];
+            if (slot.busy_valid) CUDA_OK(cudaEventSynchronize(slot.busy));        // an earlier asynchronous run_device on this slot
+            slot.busy_valid = false;
             if (need_for(wave) > slot.arena.cap) {
                 CUDA_OK(cudaStreamSynchronize(slot.stream));
                 slot.arena.reserve(need_for(wave));
                 slot.last_table_dev = nullptr;
             }
+            if (!pinned_in) dev.stage_in[s].reserve(in_host * wave);
+            if (!pinned_out) dev.stage_out[s].reserve(out_host * wave);
         }
-        std::vector<sigops_buffer> din, dout;
+        struct InFlight { int64_t i0 = 0, w = 0; bool live = false; std::vector<CopyPiece> drain; };
+        InFlight fl[kHostSlots];
+        std::vector<sigops_buffer> din, dout, hin, hout;
+        auto finish = [&](int s) {      // wave in staging buffer s: wait for its D2H, account, drain the pinned ring
+            InFlight& f = fl[s];
+            if (!f.live) return;
+            CUDA_OK(cudaEventSynchronize(dev.ev_out[s]));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, dev.ev_t[s][0], dev.ev_t[s][1]); res.h2d_ms += ms;
+            cudaEventElapsedTime(&ms, dev.ev_in[s], dev.ev_k[s]); res.gpu_ms += ms;
+            cudaEventElapsedTime(&ms, dev.ev_t[s][2], dev.ev_t[s][3]); res.d2h_ms += ms;
+            if (!f.drain.empty()) parallel_copy(f.drain, nthreads);
+            f.drain.clear();
+            f.live = false;
+        };
         int k = 0;
         for (int64_t i0 = 0; i0 < ninst; i0 += wave, ++k) {
-            Slot& slot = dev.slots[k & 1];
-            cudaStream_t st = slot.stream;
+            const int s = k % kHostSlots;
+            Slot& slot = dev.slots[s];
             const int64_t w = std::min(wave, ninst - i0);
-            if (k >= 2) {   // the slot's previous wave must have drained before its arena is reused
-                CUDA_OK(cudaStreamSynchronize(st));
-                float ms = 0;
-                cudaEventElapsedTime(&ms, slot.ev[0], slot.ev[1]); res.h2d_ms += ms;
-                cudaEventElapsedTime(&ms, slot.ev[1], slot.ev[2]); res.gpu_ms += ms;
-                cudaEventElapsedTime(&ms, slot.ev[2], slot.ev[3]); res.d2h_ms += ms;
-            }
+            finish(s);                  // the buffer's previous wave has left the device (and the pinned ring)
             slot.arena.reset();
             din.assign((size_t)w * nin, sigops_buffer{});
             dout.assign((size_t)w * nout, sigops_buffer{});
-            CUDA_OK(cudaEventRecord(slot.ev[0], st));
-            // device staging: buffer-major so that the same buffer of consecutive instances is
-            // contiguous; host runs that are contiguous too (one big batch array) become ONE copy
+            // device staging: buffer-major so that the same buffer of consecutive instances is contiguous; host
+            // runs that are contiguous too (one big batch array, or the pinned ring) become ONE copy
             for (uint32_t b = 0; b < nin; ++b)
                 for (int64_t i = 0; i < w; ++i) {
                     const sigops_buffer& hb = in[(i_begin + i0 + i) * nin + b];
@@ -1464,26 +1626,72 @@ void run_host_on_device(sigops_plan& p, int di, int64_t i_begin, int64_t i_end, 
                     db.ld = round_up(std::max<int64_t>(hb.nframes, 1), 16);
                     db.ptr = slot.arena.take_packed((size_t)db.ld * hb.nchannels * elem_size(hb.dtype));
                 }
-            res.h2d += copy_runs(in + (i_begin + i0) * nin, din.data(), w, nin, true, st);
-            CUDA_OK(cudaEventRecord(slot.ev[1], st));
+            // ---- H2D on the copy-in stream
+            const sigops_buffer* src = in + (i_begin + i0) * nin;
+            if (!pinned_in && nin) {
+                // user arrays -> pinned ring (dense, buffer-major like the device staging), by worker threads
+                hin.assign((size_t)w * nin, sigops_buffer{});
+                std::vector<CopyPiece> pieces;
+                char* cur = dev.stage_in[s].base;
+                for (uint32_t b = 0; b < nin; ++b)
+                    for (int64_t i = 0; i < w; ++i) {
+                        const sigops_buffer& ub = src[i * nin + b];
+                        sigops_buffer& hb = hin[i * nin + b];
+                        hb = ub;
+                        hb.ld = ub.nframes;
+                        hb.ptr = cur;
+                        const size_t es = elem_size(ub.dtype), row = (size_t)ub.nframes * es;
+                        for (int c = 0; c < ub.nchannels; ++c)
+                            pieces.push_back({cur + c * row, (const char*)ub.ptr + (size_t)c * ub.ld * es, row});
+                        cur += row * ub.nchannels;
+                    }
+                parallel_copy(pieces, nthreads);
+                src = hin.data();
+                ++res.staged_waves;
+            }
+            CUDA_OK(cudaEventRecord(dev.ev_t[s][0], dev.s_in));
+            res.h2d += copy_runs(src, din.data(), w, nin, true, dev.s_in, !pinned_in);
+            CUDA_OK(cudaEventRecord(dev.ev_t[s][1], dev.s_in));
+            CUDA_OK(cudaEventRecord(dev.ev_in[s], dev.s_in));
+            // ---- stages on the slot's stream
+            CUDA_OK(cudaStreamWaitEvent(slot.stream, dev.ev_in[s], 0));
             WaveIO io{w, din.data(), dout.data()};
-            res.launches += enqueue_wave(p, di, slot, st, io);
-            CUDA_OK(cudaEventRecord(slot.ev[2], st));
-            res.d2h += copy_runs(out + (i_begin + i0) * nout, dout.data(), w, nout, false, st);
-            CUDA_OK(cudaEventRecord(slot.ev[3], st));
+            res.launches += enqueue_wave(p, di, slot, slot.stream, io);
+            CUDA_OK(cudaEventRecord(dev.ev_k[s], slot.stream));
+            // ---- D2H on the copy-out stream
+            CUDA_OK(cudaStreamWaitEvent(dev.s_out, dev.ev_k[s], 0));
+            sigops_buffer* dst = out + (i_begin + i0) * nout;
+            fl[s].drain.clear();
+            if (!pinned_out) {
+                hout.assign((size_t)w * nout, sigops_buffer{});
+                char* cur = dev.stage_out[s].base;
+                for (uint32_t b = 0; b < nout; ++b)
+                    for (int64_t i = 0; i < w; ++i) {
+                        const sigops_buffer& ub = dst[i * nout + b];
+                        sigops_buffer& hb = hout[i * nout + b];
+                        hb = ub;
+                        hb.ld = ub.nframes;
+                        hb.ptr = cur;
+                        const size_t es = elem_size(ub.dtype), row = (size_t)ub.nframes * es;
+                        for (int c = 0; c < ub.nchannels; ++c)
+                            fl[s].drain.push_back({(char*)ub.ptr + (size_t)c * ub.ld * es, cur + c * row, row});
+                        cur += row * ub.nchannels;
+                    }
+                dst = hout.data();
+            }
+            CUDA_OK(cudaEventRecord(dev.ev_t[s][2], dev.s_out));
+            res.d2h += copy_runs(dst, dout.data(), w, nout, false, dev.s_out, !pinned_out);
+            CUDA_OK(cudaEventRecord(dev.ev_t[s][3], dev.s_out));
+            CUDA_OK(cudaEventRecord(dev.ev_out[s], dev.s_out));
+            fl[s].i0 = i0; fl[s].w = w; fl[s].live = true;
         }
-        for (int s = 0; s < std::min(k, 2); ++s) {
-            Slot& slot = dev.slots[s];
-            CUDA_OK(cudaStreamSynchronize(slot.stream));
-            float ms = 0;
-            cudaEventElapsedTime(&ms, slot.ev[0], slot.ev[1]); res.h2d_ms += ms;
-            cudaEventElapsedTime(&ms, slot.ev[1], slot.ev[2]); res.gpu_ms += ms;
-            cudaEventElapsedTime(&ms, slot.ev[2], slot.ev[3]); res.d2h_ms += ms;
-        }
+        for (int j = 0; j < kHostSlots; ++j) finish((k + j) % kHostSlots);      // oldest first
     } catch (const Failure& f) {
         res.code = f.code;
         res.msg = f.msg;
-        for (int s = 0; s < 2; ++s) cudaStreamSynchronize(p.ctx->devs[di].slots[s].stream);
+        for (int s = 0; s < kHostSlots; ++s) cudaStreamSynchronize(dev.slots[s].stream);
+        cudaStreamSynchronize(dev.s_in);
+        cudaStreamSynchronize(dev.s_out);
     }
 }
 
@@ -1572,10 +1780,17 @@ int sigops_ctx_create(const int* devices, int ndev, sigops_ctx** out) {
             d.ordinal = o;
             d.sm_count = prop.multiProcessorCount;
             CUDA_OK(cudaSetDevice(o));
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < kHostSlots; ++s) {
                 CUDA_OK(cudaStreamCreateWithFlags(&d.slots[s].stream, cudaStreamNonBlocking));
                 for (auto& ev : d.slots[s].ev) CUDA_OK(cudaEventCreate(&ev));
+                CUDA_OK(cudaEventCreateWithFlags(&d.slots[s].busy, cudaEventDisableTiming));
+                CUDA_OK(cudaEventCreate(&d.ev_in[s]));
+                CUDA_OK(cudaEventCreate(&d.ev_k[s]));
+                CUDA_OK(cudaEventCreate(&d.ev_out[s]));
+                for (auto& ev : d.ev_t[s]) CUDA_OK(cudaEventCreate(&ev));
             }
+            CUDA_OK(cudaStreamCreateWithFlags(&d.s_in, cudaStreamNonBlocking));
+            CUDA_OK(cudaStreamCreateWithFlags(&d.s_out, cudaStreamNonBlocking));
             ctx->devs.push_back(std::move(d));
         }
         if (const char* b = getenv("SIGOPS_WS_BYTES")) ctx->ws_budget = std::max<size_t>(size_t(64) << 20, strtoull(b, nullptr, 10));
@@ -1587,15 +1802,34 @@ void sigops_ctx_destroy(sigops_ctx* ctx) {
     if (!ctx) return;
     for (auto& d : ctx->devs) {
         cudaSetDevice(d.ordinal);
+        if (d.s_in) cudaStreamSynchronize(d.s_in);
+        if (d.s_out) cudaStreamSynchronize(d.s_out);
         for (auto& s : d.slots) {
             if (s.stream) cudaStreamSynchronize(s.stream);
+            if (s.busy_valid) cudaEventSynchronize(s.busy);
+            if (s.graph) cudaGraphExecDestroy(s.graph);
             s.arena.release();
-            if (s.pinned) cudaFreeHost(s.pinned);
+            for (int r = 0; r < kTableRing; ++r) {
+                if (s.pinned[r]) cudaFreeHost(s.pinned[r]);
+                if (s.pinned_ev[r]) cudaEventDestroy(s.pinned_ev[r]);
+            }
             for (auto& ev : s.ev)
                 if (ev) cudaEventDestroy(ev);
+            if (s.busy) cudaEventDestroy(s.busy);
             for (auto& ev : s.prof_pool) cudaEventDestroy(ev);
             if (s.stream) cudaStreamDestroy(s.stream);
         }
+        for (int s = 0; s < kHostSlots; ++s) {
+            d.stage_in[s].release();
+            d.stage_out[s].release();
+            if (d.ev_in[s]) cudaEventDestroy(d.ev_in[s]);
+            if (d.ev_k[s]) cudaEventDestroy(d.ev_k[s]);
+            if (d.ev_out[s]) cudaEventDestroy(d.ev_out[s]);
+            for (auto& ev : d.ev_t[s])
+                if (ev) cudaEventDestroy(ev);
+        }
+        if (d.s_in) cudaStreamDestroy(d.s_in);
+        if (d.s_out) cudaStreamDestroy(d.s_out);
     }
     delete ctx;
 }
@@ -1640,9 +1874,15 @@ int sigops_plan_run_device(sigops_plan* plan, int dev_index, int64_t ninst, cons
         cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : slot.stream;
         auto t0 = std::chrono::steady_clock::now();
         CUDA_OK(cudaSetDevice(dev.ordinal));
+        // every call shares this slot's workspace (temps, scalars, IIR state, BufRef table): work enqueued by an
+        // earlier call on ANOTHER stream must have finished with it first
+        if (slot.busy_valid && slot.busy_stream != st) CUDA_OK(cudaStreamWaitEvent(st, slot.busy, 0));
         if (stats) CUDA_OK(cudaEventRecord(slot.ev[4], st));
         const int64_t launches = run_device_resident(*plan, dev_index, ninst, in, out, st, slot);
         if (stats) CUDA_OK(cudaEventRecord(slot.ev[5], st));
+        CUDA_OK(cudaEventRecord(slot.busy, st));
+        slot.busy_stream = st;
+        slot.busy_valid = true;
         if (!cuda_stream || stats) CUDA_OK(cudaStreamSynchronize(st));
         if (stats) {
             memset(stats, 0, sizeof *stats);
@@ -1689,6 +1929,21 @@ int sigops_plan_run(sigops_plan* plan, int64_t ninst, const sigops_buffer* in, s
             stats->out_samples = count_out_samples(*plan, ninst);
             stats->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         }
+    });
+}
+
+int sigops_host_alloc(size_t bytes, void** out) {
+    return guarded(nullptr, [&] {
+        if (!out) fail(SIGOPS_ERR_INVALID, "null argument");
+        *out = nullptr;
+        if (bytes == 0) return;
+        CUDA_OK(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    });
+}
+
+int sigops_host_free(void* ptr) {
+    return guarded(nullptr, [&] {
+        if (ptr) CUDA_OK(cudaFreeHost(ptr));
     });
 }
 

@@ -16,7 +16,8 @@ F32, F64, I64 = 1, 2, 3
 SYMBOLS = ["sigops_abi_version", "sigops_device_count", "sigops_ctx_create", "sigops_ctx_destroy",
            "sigops_last_error", "sigops_plan_create", "sigops_plan_destroy", "sigops_plan_run",
            "sigops_plan_run_device", "sigops_plan_launch_count", "sigops_plan_algorithmic_bytes",
-           "sigops_measure_peaks", "sigops_ctx_set_profiling", "sigops_profile_collect"]
+           "sigops_measure_peaks", "sigops_ctx_set_profiling", "sigops_profile_collect",
+           "sigops_host_alloc", "sigops_host_free"]
 KERNEL_KINDS = ["map", "iir_main", "iir_carry", "iir_fix", "fir"]
 
 
@@ -73,6 +74,8 @@ def load():
     lib.sigops_measure_peaks.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.sigops_ctx_set_profiling.argtypes = [vp, C.c_int]
     lib.sigops_profile_collect.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64), C.c_int]
+    lib.sigops_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    lib.sigops_host_free.argtypes = [vp]
     if lib.sigops_abi_version() != ABI_VERSION:
         raise RuntimeError("libsignalops_cuda.so ABI version mismatch")
     _lib = lib
@@ -97,6 +100,36 @@ def dtype_code(dt):
     if dt == np.int64:
         return I64
     raise TypeError(f"host buffers must be float32, float64 or int64, not {dt}")
+
+
+class _PinnedBlock:
+    """Owner of one sigops_host_alloc block; frees it when the last array viewing it is collected
+    (the Julia glue does the same from the result array's finalizer)."""
+
+    def __init__(self, nbytes):
+        self.lib = load()
+        self.ptr = C.c_void_p()
+        _check(self.lib, None, self.lib.sigops_host_alloc(max(int(nbytes), 1), C.byref(self.ptr)))
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.sigops_host_free(self.ptr)
+                self.ptr = C.c_void_p()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype, order="F"):
+    """numpy array in page-locked memory (the result of `sink(x, GPUSink())` is allocated by the sink, so it
+    can live where the DMA engines write directly — include/signalops.h `sigops_host_alloc`)."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) if len(shape) else 1
+    blk = _PinnedBlock(n * dt.itemsize)
+    buf = (C.c_char * max(n * dt.itemsize, 1)).from_address(blk.ptr.value)
+    buf._owner = blk                                   # keeps the block alive as long as any view of `buf` exists
+    return np.frombuffer(buf, dtype=dt, count=n).reshape(shape, order=order)
 
 
 class Context:
@@ -163,8 +196,8 @@ class CompiledPlan:
         bufs = (Buffer * len(arrays))()
         for k, a in enumerate(arrays):
             n, c = (a.shape[0], 1) if a.ndim == 1 else a.shape
-            if a.ndim == 2 and c > 1 and not a.flags.f_contiguous:
-                raise ValueError("multi-channel host buffers must be column-major")
+            if a.ndim == 2 and c > 1 and n > 0 and (a.strides[1] < n * a.itemsize or a.strides[1] % a.itemsize):
+                raise ValueError("multi-channel host buffers must be column-major (channels at least nframes apart)")
             if n > 1 and a.strides[0] != a.itemsize:
                 raise ValueError("host buffers must be dense along time (stride of one element); "
                                  "copy strided views with numpy.ascontiguousarray first")

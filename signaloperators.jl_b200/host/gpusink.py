@@ -50,6 +50,14 @@ class GPUSink:
             self._plans[key] = cp
         return cp
 
+    def alloc_result(self, shape, dtype):
+        """The array `sink` returns (`initsink`, src/sink.jl:115-121).  The sink allocates it, so large results
+        are page-locked: the device writes them without the staged copy pageable memory needs."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        if nbytes >= _PIN_MIN_BYTES:
+            return cabi.pinned_empty(shape, dtype, order="F")
+        return np.empty(shape, dtype=dtype, order="F")
+
     def close(self):
         for cp in self._plans.values():
             cp.close()
@@ -74,7 +82,13 @@ def _colmajor(a):
     matrices are copied; anything already dense in Julia's column-major layout is passed as is."""
     if a.ndim == 1 or a.shape[1] == 1:
         return a if a.size <= 1 or a.strides[0] == a.itemsize else np.ascontiguousarray(a)
-    return a if a.flags.f_contiguous else np.asfortranarray(a)
+    # column-major with any leading dimension >= nframes (a view of the first rows of a taller matrix) is fine
+    ok = a.shape[0] <= 1 or (a.strides[0] == a.itemsize and a.strides[1] >= a.shape[0] * a.itemsize
+                             and a.strides[1] % a.itemsize == 0)
+    return a if ok else np.asfortranarray(a)
+
+
+_PIN_MIN_BYTES = 1 << 20
 
 
 # sample types the plan can write straight into the caller's array
@@ -95,7 +109,7 @@ def sink(x=None, to=None):
         return sink_batch(x, to)
     plan = Lowerer().build(x)
     out = plan.outputs[0]
-    data = np.empty((out.nframes, out.nchannels), dtype=np_dtype(out.dtype), order="F")
+    data = to.alloc_result((out.nframes, out.nchannels), np_dtype(out.dtype))
     if out.nframes > 0:
         cp = to.compiled(plan.tobytes())
         to.last_stats = cp.run_host(1, [_colmajor(a) for a in plan.input_arrays], [data])
@@ -165,7 +179,7 @@ def sink_batch(xs, to):
         if p.tobytes() != ref:
             raise G.SignalError(f"batch element {k} does not lower to the same plan as element 0")
     out = plans[0].outputs[0]
-    datas = [np.empty((out.nframes, out.nchannels), dtype=np_dtype(out.dtype), order="F") for _ in xs]
+    datas = [to.alloc_result((out.nframes, out.nchannels), np_dtype(out.dtype)) for _ in xs]
     if out.nframes > 0:
         cp = to.compiled(ref)
         ins = [_colmajor(a) for p in plans for a in p.input_arrays]

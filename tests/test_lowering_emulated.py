@@ -29,6 +29,9 @@ class EmulatedSink(GPUSink):
     def compiled(self, plan_bytes):
         return _EmuPlan(plan_bytes)
 
+    def alloc_result(self, shape, dtype):          # no CUDA driver here: plain pageable memory
+        return np.empty(shape, dtype=dtype, order="F")
+
 
 @pytest.fixture(scope="module")
 def gpu():

@@ -9,6 +9,7 @@ info)
 link) python tools/host_link_probe.py 2>&1 | tee gpurun_out/host_link.txt ;;
 dmma) ./tools/dmma_peak 2>&1 | tee gpurun_out/dmma_peak.txt ;;
 tests) python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ;;
+hosttests) python -m pytest tests/test_gpu_hostpath.py -m gpu -x -q 2>&1 | tail -25 ;;
 firtests) python -m pytest tests/test_gpu_fir_mma.py tests/test_gpu_resample_full.py tests/test_resample_analytic.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -25 ;;
 bench) python bench.py --steps 20 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; tail -c 6000 gpurun_out/bench_n1.json; tail -5 gpurun_out/bench_n1.err ;;
 benchref) python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json; tail -c 1500 gpurun_out/bench_ref.json ;;
