@@ -50,7 +50,13 @@ constexpr int kTmSubBytes = 32 * 128;                    // one box row block: 3
 // Float32 shape: the bytes per sample halve while the FP64 work per sample stays, so the kernel is
 // bound by its dependency chains — twice the warps, 3-block stages (96 frames, 384 bytes per row)
 constexpr int kTmSubsPerStageF32 = 3, kTmWarpsF32 = 8;
-constexpr size_t tm_smem_bytes(int nw, int ns, int subs) { return (size_t)nw * ns * subs * kTmSubBytes + 1024; }   // + 1024-byte alignment slack
+// fused row-invariant programs (config 5: 5 general biquads + 4 elementwise operations per sample): the FP64
+// dependency chains are long, so twice the warps on 48-frame stages, like the Float32 shape
+constexpr int kTmSubsPerStageLv = 3, kTmWarpsLv = 8;
+constexpr int kTmMaxLeafOps = 4;                        // fused row-invariant operations before / after the cascade
+constexpr size_t tm_smem_bytes(int nw, int ns, int subs, bool lv = false, int sub = kTmSub) {   // + 1024-byte alignment slack
+    return (size_t)nw * ns * subs * kTmSubBytes + 1024 + (lv ? (size_t)nw * 2 * kTmMaxLeafOps * subs * sub * sizeof(double) : 0);
+}
 
 struct IirTmapParams {
     const BufRef* bufrefs;
@@ -64,6 +70,11 @@ struct IirTmapParams {
     int64_t nunits;            // row groups * cpr
     double gain, scale;
     double coef[kIirMaxSections][5];
+    // Fused elementwise programs whose leaves do not depend on the row (constants, generators, ramps — e.g.
+    // BASELINE config 5: x * (0.5 sin + 0.5) before the cascade, y * ramp_on * ramp_off + tone after it):
+    // ops[0 .. n_in_ops) combine the loaded sample with their leaf, ops[4 .. 4 + n_ep_ops) the filter output.
+    int n_in_ops, n_ep_ops;
+    sigops_instr ops[2 * kTmMaxLeafOps];
 };
 
 __device__ __forceinline__ void tmap_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
@@ -84,8 +95,31 @@ __device__ __forceinline__ void tmap_store_3d(const CUtensorMap* tm, int c0, int
 // chunks each); samples are widened on load, the state and all arithmetic stay Float64 like the
 // reference's DF2T filter state, and results are rounded on store.
 // Returns sum(out^2) over the first `nvalid` outputs as stored.
-template <int M, bool UNITB, class T>
-__device__ __forceinline__ double cascade16_swz(Cascade<M>& f, unsigned char* row, int key, int blk, double gain, double sc, int nvalid) {
+// acc[k] = acc[k] (op) v[k] for 16 frames, the operator decoded once (v: warp-uniform values in shared memory)
+__device__ __forceinline__ void apply_leaf16(int op, double* acc, const double* v) {
+    switch (op) {
+        case SIGOPS_OP_ADD:
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc[k] = acc[k] + v[k];
+            break;
+        case SIGOPS_OP_SUB:
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc[k] = acc[k] - v[k];
+            break;
+        case SIGOPS_OP_MUL:
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc[k] = acc[k] * v[k];
+            break;
+        default:
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc[k] = acc[k] / v[k];
+            break;
+    }
+}
+
+template <int M, bool UNITB, class T, bool LV = false>
+__device__ __forceinline__ double cascade16_swz(Cascade<M>& f, unsigned char* row, int key, int blk, double gain, double sc, int nvalid,
+                                                const IirTmapParams* P = nullptr, const double* lv = nullptr, int lvpitch = 0) {
     double xr[16];
     if (sizeof(T) == 8) {
 #pragma unroll
@@ -100,6 +134,9 @@ __device__ __forceinline__ double cascade16_swz(Cascade<M>& f, unsigned char* ro
             xr[4 * j] = v.x; xr[4 * j + 1] = v.y; xr[4 * j + 2] = v.z; xr[4 * j + 3] = v.w;
         }
     }
+    if (LV) {
+        for (int j = 0; j < P->n_in_ops; ++j) apply_leaf16(P->ops[j].op, xr, lv + j * lvpitch);
+    }
     double pipe[M], out[16];
 #pragma unroll
     for (int t = 0; t < 16 + M - 1; ++t) {
@@ -112,6 +149,10 @@ __device__ __forceinline__ double cascade16_swz(Cascade<M>& f, unsigned char* ro
                 if (j == M - 1) out[k] = (pipe[j] * gain) * sc;
             }
         }
+    }
+    if (LV) {
+        for (int j = 0; j < P->n_ep_ops; ++j)
+            apply_leaf16(P->ops[kTmMaxLeafOps + j].op, out, lv + (kTmMaxLeafOps + j) * lvpitch);
     }
     if (sizeof(T) == 8) {
 #pragma unroll
@@ -133,7 +174,12 @@ __device__ __forceinline__ double cascade16_swz(Cascade<M>& f, unsigned char* ro
 
 // NW warps per block, NS stages per warp (NS - 1 loads in flight while one stage is filtered), SUBS
 // 128-byte blocks per row and stage (odd: keeps the swizzle key distinct for 8 consecutive rows).
-template <int M, bool UNITB, int NW, int NS, int SUBS, class T>
+// value of a row-invariant leaf at frame n (the interpreter's exact per-frame formulas)
+__device__ __forceinline__ double rowinv_leaf(const sigops_instr* I, int64_t n) {
+    return I->leaf == SIGOPS_LEAF_CONST ? I->d0 : leaf_value_slow(I, nullptr, n, 0);
+}
+
+template <int M, bool UNITB, int NW, int NS, int SUBS, class T, bool LV = false>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUtensorMap tm_in,
            const __grid_constant__ CUtensorMap tm_out) {
@@ -147,6 +193,8 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tm_smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* const stage0 = base + (size_t)warp * NS * kStageB;
     auto stage_of = [&](int b) { return stage0 + b * kStageB; };
+    // (LV) the warp's leaf vectors: [2 * kTmMaxLeafOps][SC] doubles, the same for all 32 rows of the warp
+    double* const lvbuf = reinterpret_cast<double*>(base + (size_t)NW * NS * kStageB) + (size_t)warp * 2 * kTmMaxLeafOps * SC;
 
     const int64_t unit = (int64_t)blockIdx.x * NW + warp;             // (row group, chunk)
     if (unit >= P.nunits) return;
@@ -202,13 +250,24 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
         unsigned char* rowp = stage_of(b) + lane * (SUBS * 128);
         const bool keep = off >= pre;                                  // pre is a multiple of the stage
         double s3 = 0.0;
+        if (LV) {
+            // the leaves of the fused programs depend on the frame only: every lane evaluates a few frames of the
+            // stage (the interpreter's exact formulas), all 32 rows then read them back as broadcasts
+            __syncwarp();
+            for (int j = 0; j < P.n_in_ops; ++j)
+                for (int fr = lane; fr < SC; fr += 32) lvbuf[j * SC + fr] = rowinv_leaf(&P.ops[j], start + off + fr);
+            for (int j = 0; j < P.n_ep_ops; ++j)
+                for (int fr = lane; fr < SC; fr += 32)
+                    lvbuf[(kTmMaxLeafOps + j) * SC + fr] = rowinv_leaf(&P.ops[kTmMaxLeafOps + j], start + off + fr);
+            __syncwarp();
+        }
 #pragma unroll
         for (int s = 0; s < SUBS; ++s) {
 #pragma unroll
             for (int blk = 0; blk < SUB / 16; ++blk) {
                 const int64_t rem = work - off - s * SUB - blk * 16;   // outputs of this block that exist
-                s3 += cascade16_swz<M, UNITB, T>(f, rowp + s * 128, (SUBS * lane + s) & 7, blk, P.gain, P.scale,
-                                                 rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0));
+                s3 += cascade16_swz<M, UNITB, T, LV>(f, rowp + s * 128, (SUBS * lane + s) & 7, blk, P.gain, P.scale,
+                                                     rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0), &P, lvbuf + s * SUB + blk * 16, SC);
             }
             if (s == 0 && h + NS - 1 < nstage) {
                 // the stage filtered one iteration ago went to a tensor store: once the TMA unit has

@@ -22,22 +22,24 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-template <int M, int NW, int NS, int SUBS, class T>
+template <int M, int NW, int NS, int SUBS, class T, bool LV>
 void launch_cfg(bool unitb, dim3 grid, cudaStream_t st, const IirTmapParams& P, const CUtensorMap& a, const CUtensorMap& b) {
-    constexpr size_t smem = tm_smem_bytes(NW, NS, SUBS);
+    constexpr size_t smem = tm_smem_bytes(NW, NS, SUBS, LV, 128 / (int)sizeof(T));
     if (unitb) {
-        ensure_dyn_smem(k_iir_tmap<M, true, NW, NS, SUBS, T>, smem);
-        k_iir_tmap<M, true, NW, NS, SUBS, T><<<grid, NW * 32, smem, st>>>(P, a, b);
+        ensure_dyn_smem(k_iir_tmap<M, true, NW, NS, SUBS, T, LV>, smem);
+        k_iir_tmap<M, true, NW, NS, SUBS, T, LV><<<grid, NW * 32, smem, st>>>(P, a, b);
     } else {
-        ensure_dyn_smem(k_iir_tmap<M, false, NW, NS, SUBS, T>, smem);
-        k_iir_tmap<M, false, NW, NS, SUBS, T><<<grid, NW * 32, smem, st>>>(P, a, b);
+        ensure_dyn_smem(k_iir_tmap<M, false, NW, NS, SUBS, T, LV>, smem);
+        k_iir_tmap<M, false, NW, NS, SUBS, T, LV><<<grid, NW * 32, smem, st>>>(P, a, b);
     }
 }
 
 template <int M>
 void launch_m(bool f32, bool unitb, dim3 grid, cudaStream_t st, const IirTmapParams& P, const CUtensorMap& a, const CUtensorMap& b) {
-    if (f32) launch_cfg<M, kTmWarpsF32, kTmStages, kTmSubsPerStageF32, float>(unitb, grid, st, P, a, b);
-    else launch_cfg<M, kTmWarps, kTmStages, kTmSubsPerStage, double>(unitb, grid, st, P, a, b);
+    const bool lv = P.n_in_ops + P.n_ep_ops > 0;
+    if (f32) launch_cfg<M, kTmWarpsF32, kTmStages, kTmSubsPerStageF32, float, false>(unitb, grid, st, P, a, b);
+    else if (lv) launch_cfg<M, kTmWarpsLv, kTmStages, kTmSubsPerStageLv, double, true>(unitb, grid, st, P, a, b);
+    else launch_cfg<M, kTmWarps, kTmStages, kTmSubsPerStage, double, false>(unitb, grid, st, P, a, b);
 }
 
 }  // namespace
@@ -47,13 +49,13 @@ bool iir_tmap_available() { return encode_fn() != nullptr; }
 // [rows][frames] matrix of Float64 (elem_bytes 8) or Float32 (4) samples, row r at
 // base + r*row_stride_bytes, described as [row][frame/S][S] with S = 128 bytes of samples;
 // box = (S, blocks per stage, 32), 128-byte swizzle.  `frames` must be a multiple of S.
-bool iir_tmap_encode(void* out_map, void* base, int64_t frames, int64_t rows, int64_t row_stride_bytes, int elem_bytes) {
+bool iir_tmap_encode(void* out_map, void* base, int64_t frames, int64_t rows, int64_t row_stride_bytes, int elem_bytes, int subs_override) {
     EncodeTiledFn fn = encode_fn();
     const int S = 128 / elem_bytes;
     if (!fn || (elem_bytes != 4 && elem_bytes != 8) || frames % S) return false;
     const cuuint64_t gdim[3] = {(cuuint64_t)S, (cuuint64_t)(frames / S), (cuuint64_t)rows};
     const cuuint64_t gstr[2] = {128, (cuuint64_t)row_stride_bytes};
-    const cuuint32_t box[3] = {(cuuint32_t)S, (cuuint32_t)(elem_bytes == 8 ? kTmSubsPerStage : kTmSubsPerStageF32), 32u};
+    const cuuint32_t box[3] = {(cuuint32_t)S, (cuuint32_t)(subs_override > 0 ? subs_override : (elem_bytes == 8 ? kTmSubsPerStage : kTmSubsPerStageF32)), 32u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     const CUresult r = fn((CUtensorMap*)out_map, elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base,
                           gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

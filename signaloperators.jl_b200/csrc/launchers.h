@@ -24,7 +24,7 @@ struct IirTmapParams;
 struct alignas(64) TensorMapBlob { unsigned char bytes[128]; };
 bool iir_tmap_available();
 bool tmap_encode_2d_f64(void* out_map, void* base, int64_t dim0, int64_t rows, int64_t row_stride_bytes, int box0, int box1);
-bool iir_tmap_encode(void* out_map, void* base, int64_t frames, int64_t rows, int64_t row_stride_bytes, int elem_bytes);
+bool iir_tmap_encode(void* out_map, void* base, int64_t frames, int64_t rows, int64_t row_stride_bytes, int elem_bytes, int subs_override = 0);
 #ifndef TMW
 #define TMW 4
 #define TMS 2

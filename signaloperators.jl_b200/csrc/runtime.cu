@@ -186,6 +186,8 @@ struct IirDerived {
     bool fast32 = false;           // same shape on Float32 buffers: k_iir_tmap<float> applies
     bool tma_prog = false;         // k_iir_tma<PROG>: one plain f64 buffer + buffer-free programs
     int prog_in_start = 0, prog_in_len = 0;   // input program with the buffer leaf turned into LEAF_STAGE
+    bool rowinv = false;           // tma_prog whose other leaves depend on the frame only: k_iir_tmap with leaf vectors
+    std::vector<sigops_instr> rv_in, rv_ep;   // those operations, in order (<= kTmMaxLeafOps each)
     bool unitb = false;            // every section has b0 == 1 and b2 == 1 exactly
     int n_scale = 0;
     double scale[2] = {1.0, 1.0};
@@ -446,6 +448,24 @@ void derive_iir(sigops_plan& p, StageRT& s, int idx) {
                 p.instrs.push_back(I);
             }
             if (s.iir.prog_in_len == 1) s.iir.prog_in_len = 0;      // bare load: nothing to evaluate
+            // Row-invariant form: `LOAD buffer, (op leaf)*` before and `LOAD stage, (op leaf)*` after the cascade,
+            // every leaf a constant, generator or ramp (the same value for all rows at a frame)
+            auto rowinv_ops = [&](int start, int len, std::vector<sigops_instr>& ops) {
+                for (int i = 1; i < len; ++i) {
+                    const sigops_instr& I = p.instrs[start + i];
+                    if (I.op < SIGOPS_OP_ADD || I.op > SIGOPS_OP_DIV) return false;
+                    if (I.leaf != SIGOPS_LEAF_CONST && I.leaf != SIGOPS_LEAF_GEN && I.leaf != SIGOPS_LEAF_RAMP_ON &&
+                        I.leaf != SIGOPS_LEAF_RAMP_OFF)
+                        return false;
+                    ops.push_back(I);
+                }
+                return (int)ops.size() <= kTmMaxLeafOps;
+            };
+            const bool in_first = bufpc == st.in_prog_start && p.instrs[bufpc].op == SIGOPS_OP_LOAD;
+            const bool ep_first = st.epi_prog_len == 0 || (p.instrs[st.epi_prog_start].op == SIGOPS_OP_LOAD &&
+                                                           p.instrs[st.epi_prog_start].leaf == SIGOPS_LEAF_STAGE);
+            s.iir.rowinv = in_first && ep_first && rowinv_ops(st.in_prog_start, st.in_prog_len, s.iir.rv_in) &&
+                           rowinv_ops(st.epi_prog_start, st.epi_prog_len, s.iir.rv_ep);
         }
     }
 }
@@ -976,9 +996,11 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
             // tensor, or the library's own staging), enough rows to fill warps, and a filter that decays
             // within a chunk (WARM).
             const bool f32 = s.iir.fast32;
+            const bool rowinv_pre = tma && s.iir.tma_prog && s.iir.rowinv && !getenv("SIGOPS_NO_TMAP_LEAVES");
             const int esz = f32 ? 4 : 8;
-            const int stage_cols = f32 ? 32 * kTmSubsPerStageF32 : kTmStageCols;
-            if (((tma && s.iir.fast && !s.iir.tma_prog) || f32) && !getenv("SIGOPS_NO_TMAP") && iir_tmap_available() &&
+            const int stage_cols = f32 ? 32 * kTmSubsPerStageF32 : (rowinv_pre ? kTmSub * kTmSubsPerStageLv : kTmStageCols);
+            const bool rowinv = rowinv_pre;
+            if (((tma && s.iir.fast && !s.iir.tma_prog) || f32 || rowinv) && !getenv("SIGOPS_NO_TMAP") && iir_tmap_available() &&
                 (rows % 32 == 0 || rows >= 256) && rows * 32 < (int64_t(1) << 31) && g.n_out < (int64_t(1) << 30)) {
                 const BufRef* refs = (const BufRef*)slot.last_table.data();
                 auto uniform = [&](int b, char*& base, int64_t& stride) {
@@ -1001,7 +1023,7 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                 if (uniform(s.iir.plain_buf, bin, sin_) && uniform(g.out_buf, bout, sout) && 2 * Wst <= g.n_out) {
                     // chunk length: whole waves of one block (8 warps = 8 units) per SM; a unit walks L + Wc frames
                     const int64_t N = g.n_out, groups = (rows + 31) / 32;
-                    const int nw = f32 ? kTmWarpsF32 : kTmWarps;
+                    const int nw = f32 ? kTmWarpsF32 : (rowinv ? kTmWarpsLv : kTmWarps);
                     const int64_t jmax = std::max<int64_t>(1, (N + stage_cols - 1) / stage_cols);
                     double best = 1e300;
                     int64_t bestL = 0;
@@ -1021,9 +1043,9 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                                            choose_iir_chunking_flat(s, rows, dev.sm_count).cost * frame_cycles(32 * kTmaWarps);
                     TensorMapBlob mi, mo;
                     // (a Float32 stage has no other fast kernel to fall back on: take this one whenever it applies)
-                    if (bestL > Wst && (tmap_wins || f32) &&
-                        iir_tmap_encode(&mi, bin, std::min<int64_t>(s.iir.plain_len, N), rows, sin_, esz) &&
-                        iir_tmap_encode(&mo, bout, N, rows, sout, esz)) {
+                    if (bestL > Wst && (tmap_wins || f32 || rowinv) &&
+                        iir_tmap_encode(&mi, bin, std::min<int64_t>(s.iir.plain_len, N), rows, sin_, esz, rowinv ? kTmSubsPerStageLv : 0) &&
+                        iir_tmap_encode(&mo, bout, N, rows, sout, esz, rowinv ? kTmSubsPerStageLv : 0)) {
                         IirTmapParams T{};
                         T.bufrefs = d_refs; T.scalars = scalars; T.nbuf = nbuf; T.nscalars = nscal;
                         T.out_buf = g.out_buf; T.sumsq_slot = g.sumsq_slot; T.nch = g.nchannels; T.nrows = rows;
@@ -1032,6 +1054,13 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                         T.nunits = groups * T.cpr;
                         T.gain = g.gain;
                         T.scale = s.iir.scale[0] * s.iir.scale[1];
+                        if (rowinv) {
+                            T.scale = 1.0;
+                            T.n_in_ops = (int)s.iir.rv_in.size();
+                            T.n_ep_ops = (int)s.iir.rv_ep.size();
+                            for (int j = 0; j < T.n_in_ops; ++j) T.ops[j] = s.iir.rv_in[j];
+                            for (int j = 0; j < T.n_ep_ops; ++j) T.ops[kTmMaxLeafOps + j] = s.iir.rv_ep[j];
+                        }
                         const double* tc = p.blob.data() + p.tables[g.coef_table].offset;
                         for (int j = 0; j < s.iir.M; ++j)
                             for (int k = 0; k < 5; ++k) T.coef[j][k] = tc[j * 5 + k];
@@ -1039,7 +1068,8 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                         const bool unitb = s.iir.unitb;
                         dim3 tgrid((unsigned)((T.nunits + nw - 1) / nw));
                         if (getenv("SIGOPS_DEBUG"))
-                            fprintf(stderr, "[sigops] IIR stage %zu: tensor-map%s rows=%lld N=%lld M=%d W=%lld L=%lld chunks/row=%lld blocks=%u\n", si, f32 ? " (Float32)" : "",
+                            fprintf(stderr, "[sigops] IIR stage %zu: tensor-map%s rows=%lld N=%lld M=%d W=%lld L=%lld chunks/row=%lld blocks=%u\n", si,
+                                    f32 ? " (Float32)" : (rowinv ? " (fused row-invariant programs)" : ""),
                                     (long long)rows, (long long)N, M_, (long long)s.iir.W, (long long)T.L, (long long)T.cpr, tgrid.x);
                         add(KIND_IIR_MAIN, [=](cudaStream_t st) { launch_iir_tmap(f32, M_, unitb, tgrid, st, T, &mi, &mo); });
                         continue;

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle
-from signalops import Amplify, Filt, Highpass, Lowpass, Normpower, Pad, Signal, Until, dB, kHz, s, sink_batch, zero
+from signalops import Amplify, Filt, Highpass, Hz, Lowpass, Normpower, Pad, Signal, Until, dB, kHz, s, sink_batch, zero
 
 pytestmark = pytest.mark.gpu
 F64_TOL = 1e-9
@@ -107,3 +107,33 @@ def test_padded_input_through_the_tensor_map_kernel(gpu):
         assert np.max(np.abs(a[k][0] - b[k][0])) <= 1e-12 * rms(b[k][0])
     want, _ = oracle.sink(chain(xs[7]))
     assert np.max(np.abs(a[7][0] - want)) <= F64_TOL * rms(want)
+
+
+def test_fused_row_invariant_programs(gpu):
+    """BASELINE config 5's shape on the tensor-map kernel: AM noise |> Filt(Bandpass) |> Ramp |> Mix(tone) with the
+    modulator, the ramps and the tone (all functions of the frame only) evaluated once per warp and stage —
+    src/functions.jl:53-60, src/ramps.jl:56-72, src/filters.jl:221-262.  One launch, one HBM round trip."""
+    import os
+    from signalops import AffineSin, Bandpass, Mix, Ramp, Until, ms, s, sin, sink_batch
+    rng = np.random.default_rng(55)
+    xs = [rng.standard_normal((96000, 32)) for _ in range(3)]          # 96 rows, 1 s at 96 kHz
+
+    def chain(x):
+        am = Amplify(Signal(x, 96 * kHz), Signal(AffineSin(0.5, 0.5), ω=5 * Hz)) >> Until(1 * s)
+        return am >> Filt(Bandpass, 500 * Hz, 4 * kHz) >> Ramp(10 * ms) >> Mix(Signal(sin, ω=1 * kHz) >> Until(1 * s))
+
+    got = sink_batch([chain(x) for x in xs], gpu)
+    assert gpu.last_stats["launches"] == 1
+    old = os.environ.get("SIGOPS_NO_TMAP_LEAVES")
+    os.environ["SIGOPS_NO_TMAP_LEAVES"] = "1"
+    try:
+        ref = sink_batch([chain(x) for x in xs], gpu)
+    finally:
+        os.environ.pop("SIGOPS_NO_TMAP_LEAVES")
+        if old is not None:
+            os.environ["SIGOPS_NO_TMAP_LEAVES"] = old
+    for k in range(3):
+        assert got[k][0].shape == (96000, 32) and got[k][1] == 96000.0
+        assert np.max(np.abs(got[k][0] - ref[k][0])) <= 1e-11 * rms(ref[k][0])
+    want, _ = oracle.sink(chain(xs[1]))
+    assert np.max(np.abs(got[1][0] - want)) <= F64_TOL * rms(want)
