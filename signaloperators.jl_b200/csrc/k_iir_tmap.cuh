@@ -254,11 +254,18 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
             // the leaves of the fused programs depend on the frame only: every lane evaluates a few frames of the
             // stage (the interpreter's exact formulas), all 32 rows then read them back as broadcasts
             __syncwarp();
-            for (int j = 0; j < P.n_in_ops; ++j)
-                for (int fr = lane; fr < SC; fr += 32) lvbuf[j * SC + fr] = rowinv_leaf(&P.ops[j], start + off + fr);
-            for (int j = 0; j < P.n_ep_ops; ++j)
-                for (int fr = lane; fr < SC; fr += 32)
-                    lvbuf[(kTmMaxLeafOps + j) * SC + fr] = rowinv_leaf(&P.ops[kTmMaxLeafOps + j], start + off + fr);
+            // (measured on config 5: replacing the per-frame sin() of the generators by angle additions across
+            //  stages does not change the run time — the kernel is bound by the FP64 dependency chains of the
+            //  cascade, not by these 6 evaluations per lane and stage — so the exact formulas stay)
+            for (int jj = 0; jj < P.n_in_ops + P.n_ep_ops; ++jj) {
+                const int j = jj < P.n_in_ops ? jj : kTmMaxLeafOps + jj - P.n_in_ops;
+                const sigops_instr* I = &P.ops[j];
+                const int64_t n0 = start + off;
+                bool ones = false;                                     // ramps are 1 outside a short region
+                if (I->leaf == SIGOPS_LEAF_RAMP_ON) ones = n0 + I->i0 > I->i1;
+                else if (I->leaf == SIGOPS_LEAF_RAMP_OFF) ones = n0 + (SC - 1) + I->i0 <= I->i1;
+                for (int fr = lane; fr < SC; fr += 32) lvbuf[j * SC + fr] = ones ? 1.0 : rowinv_leaf(I, n0 + fr);
+            }
             __syncwarp();
         }
 #pragma unroll
