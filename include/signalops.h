@@ -45,6 +45,13 @@ extern "C" {
 #define SIGOPS_F32 1
 #define SIGOPS_F64 2
 #define SIGOPS_I64 3
+#define SIGOPS_I16 4                 /* PCM16: only as the file-side encoding of an interleaved host buffer */
+/* Host buffers of sigops_plan_run may be given in WAV data-chunk layout: OR this into `dtype`.  The
+ * buffer is then frame-interleaved ([frame][channel], `ld` ignored) in the encoding of the low byte
+ * (F32 / F64 / I16) and the library transposes and converts on the device — results leave the GPU
+ * already in file layout (`sink(x,"file.wav")`, src/sink.jl:139-142 + src/WAV.jl:3-7), files enter it
+ * as they are on disk (`Signal("file.wav")`, src/WAV.jl:8-15).  The plan's buffer must be F32 or F64. */
+#define SIGOPS_INTERLEAVED 0x100
 
 typedef struct sigops_ctx sigops_ctx;
 typedef struct sigops_plan sigops_plan;

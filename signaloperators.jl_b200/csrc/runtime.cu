@@ -30,6 +30,7 @@
 #include "k_fir_tmap.cuh"
 #include "k_iir_tmap.cuh"
 #include "k_map.cuh"
+#include "k_wav.cuh"
 
 static_assert(sizeof(sigops_instr) == 80, "ABI: sigops_instr");
 static_assert(sizeof(sigops_piece) == 32, "ABI: sigops_piece");
@@ -43,7 +44,7 @@ namespace {
 
 thread_local std::string g_tls_error = "";
 
-size_t elem_size(int dtype) { return dtype == SIGOPS_F32 ? 4 : 8; }
+size_t elem_size(int dtype) { return (dtype & 0xff) == SIGOPS_F32 ? 4 : ((dtype & 0xff) == SIGOPS_I16 ? 2 : 8); }
 int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 // Grow-only device arena (one per pipeline slot); reset at the start of a wave.
@@ -1420,7 +1421,7 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
     return replay();
 }
 
-void validate_io(const sigops_plan& p, int64_t ninst, const sigops_buffer* in, const sigops_buffer* out) {
+void validate_io(const sigops_plan& p, int64_t ninst, const sigops_buffer* in, const sigops_buffer* out, bool allow_wav = false) {
     if (ninst < 0) fail(SIGOPS_ERR_INVALID, "negative instance count");
     if (ninst > 0 && ((p.h.n_inputs && !in) || !out)) fail(SIGOPS_ERR_INVALID, "null buffer array");
     for (int64_t i = 0; i < ninst; ++i) {
@@ -1428,11 +1429,16 @@ void validate_io(const sigops_plan& p, int64_t ninst, const sigops_buffer* in, c
             const bool isin = b < p.h.n_inputs;
             const sigops_buffer& ub = isin ? in[i * p.h.n_inputs + b] : out[i * p.h.n_outputs + (b - p.h.n_inputs)];
             const sigops_bufdesc& bd = isin ? p.bufs[b] : p.bufs[p.h.n_temps + b];
-            if (ub.nframes != bd.nframes || ub.nchannels != bd.nchannels || ub.dtype != bd.dtype)
+            const bool wav = (ub.dtype & SIGOPS_INTERLEAVED) != 0;
+            const int enc = ub.dtype & 0xff;
+            const bool type_ok = wav ? (allow_wav && (enc == SIGOPS_F32 || enc == SIGOPS_F64 || enc == SIGOPS_I16) &&
+                                        (bd.dtype == SIGOPS_F32 || bd.dtype == SIGOPS_F64))
+                                     : ub.dtype == bd.dtype;
+            if (ub.nframes != bd.nframes || ub.nchannels != bd.nchannels || !type_ok)
                 fail(SIGOPS_ERR_INVALID, "instance %lld %s %u: buffer is %lldx%d type %d, plan expects %lldx%d type %d",
                      (long long)i, isin ? "input" : "output", isin ? b : b - p.h.n_inputs, (long long)ub.nframes, ub.nchannels,
                      ub.dtype, (long long)bd.nframes, bd.nchannels, bd.dtype);
-            if (ub.ld < ub.nframes) fail(SIGOPS_ERR_INVALID, "instance %lld: ld %lld < nframes %lld", (long long)i, (long long)ub.ld, (long long)ub.nframes);
+            if (!wav && ub.ld < ub.nframes) fail(SIGOPS_ERR_INVALID, "instance %lld: ld %lld < nframes %lld", (long long)i, (long long)ub.ld, (long long)ub.nframes);
             if (!ub.ptr && ub.nframes > 0) fail(SIGOPS_ERR_INVALID, "instance %lld: null buffer pointer", (long long)i);
         }
     }
@@ -1579,6 +1585,11 @@ void run_host_on_device(sigops_plan& p, int di, int64_t i_begin, int64_t i_end, 
             io_bytes += (size_t)round_up(round_up(std::max<int64_t>(bd.nframes, 1), 16) * bd.nchannels * (int64_t)elem_size(bd.dtype), 256);
             (b < nin ? in_host : out_host) += (size_t)bd.nframes * bd.nchannels * elem_size(bd.dtype);
         }
+        // WAV-layout host buffers need a device scratch area next to the planar buffer
+        bool any_wav = false;
+        for (uint32_t b = 0; b < nin; ++b) any_wav = any_wav || (in[i_begin * nin + b].dtype & SIGOPS_INTERLEAVED);
+        for (uint32_t b = 0; b < nout; ++b) any_wav = any_wav || (out[i_begin * nout + b].dtype & SIGOPS_INTERLEAVED);
+        if (any_wav) { io_bytes *= 2; in_host *= 2; out_host *= 2; }   // (a Float64 file for a Float32 plan buffer is twice its size)
         // page-locked caller memory is copied from / to directly; anything else goes through the pinned ring
         bool pinned_in = true, pinned_out = true;
         for (int64_t i : {i_begin, i_end - 1}) {
@@ -1616,7 +1627,11 @@ void run_host_on_device(sigops_plan& p, int di, int64_t i_begin, int64_t i_end, 
         }
         struct InFlight { int64_t i0 = 0, w = 0; bool live = false; std::vector<CopyPiece> drain; };
         InFlight fl[kHostSlots];
-        std::vector<sigops_buffer> din, dout, hin, hout;
+        // din/dout: the planar device buffers the stages see; c*_u / c*_d: what is copied (the same buffer, or for
+        // a WAV-layout host buffer its raw interleaved bytes and a device scratch area next to the planar one)
+        std::vector<sigops_buffer> din, dout, cin_u, cin_d, cout_u, cout_d, hin, hout;
+        struct WavJob { WavParams P; };
+        std::vector<WavJob> wav_in, wav_out;
         auto finish = [&](int s) {      // wave in staging buffer s: wait for its D2H, account, drain the pinned ring
             InFlight& f = fl[s];
             if (!f.live) return;
@@ -1629,6 +1644,68 @@ void run_host_on_device(sigops_plan& p, int di, int64_t i_begin, int64_t i_end, 
             f.drain.clear();
             f.live = false;
         };
+        // device staging of one side of a wave: planar buffers first (buffer-major: the same buffer of consecutive
+        // instances is contiguous, which the tensor-map kernels and merged copies rely on), WAV scratch after them
+        auto stage_side = [&](Slot& slot, const sigops_buffer* user, int64_t w, uint32_t nb, uint32_t desc0, bool input,
+                              std::vector<sigops_buffer>& dbufs, std::vector<sigops_buffer>& cu, std::vector<sigops_buffer>& cd,
+                              std::vector<WavJob>& jobs) {
+            dbufs.assign((size_t)w * nb, sigops_buffer{});
+            cu.assign((size_t)w * nb, sigops_buffer{});
+            cd.assign((size_t)w * nb, sigops_buffer{});
+            jobs.clear();
+            for (uint32_t b = 0; b < nb; ++b)
+                for (int64_t i = 0; i < w; ++i) {
+                    const sigops_buffer& ub = user[i * nb + b];
+                    const sigops_bufdesc& bd = p.bufs[desc0 + b];
+                    sigops_buffer& db = dbufs[i * nb + b];
+                    db = ub;
+                    db.dtype = bd.dtype;
+                    db.ld = round_up(std::max<int64_t>(ub.nframes, 1), 16);
+                    db.ptr = slot.arena.take_packed((size_t)db.ld * ub.nchannels * elem_size(bd.dtype));
+                    cu[i * nb + b] = ub;
+                    cd[i * nb + b] = db;
+                }
+            for (uint32_t b = 0; b < nb; ++b)
+                for (int64_t i = 0; i < w; ++i) {
+                    const sigops_buffer& ub = user[i * nb + b];
+                    if (!(ub.dtype & SIGOPS_INTERLEAVED)) continue;
+                    const int enc = ub.dtype & 0xff;
+                    const int64_t total = ub.nframes * ub.nchannels;
+                    void* scratch = slot.arena.take_packed((size_t)std::max<int64_t>(total, 1) * elem_size(enc));
+                    cu[i * nb + b] = sigops_buffer{ub.ptr, total, 1, enc, total};
+                    cd[i * nb + b] = sigops_buffer{scratch, total, 1, enc, total};
+                    const sigops_buffer& db = dbufs[i * nb + b];
+                    WavParams W{};
+                    W.src = input ? scratch : db.ptr;
+                    W.dst = input ? db.ptr : scratch;
+                    W.nframes = ub.nframes; W.nch = ub.nchannels; W.ld = db.ld;
+                    W.planar_dtype = db.dtype; W.file_dtype = enc;
+                    jobs.push_back({W});
+                }
+        };
+        // dense copy of the copy views into / out of the pinned ring (one piece per channel row)
+        auto ring_views = [&](char* ring, const std::vector<sigops_buffer>& cu, int64_t w, uint32_t nb, std::vector<sigops_buffer>& hv,
+                              std::vector<CopyPiece>& pieces, bool to_ring) {
+            hv.assign((size_t)w * nb, sigops_buffer{});
+            pieces.clear();
+            char* cur = ring;
+            for (uint32_t b = 0; b < nb; ++b)
+                for (int64_t i = 0; i < w; ++i) {
+                    const sigops_buffer& ub = cu[i * nb + b];
+                    sigops_buffer& hb = hv[i * nb + b];
+                    hb = ub;
+                    hb.ld = ub.nframes;
+                    hb.ptr = cur;
+                    const size_t es = elem_size(ub.dtype), row = (size_t)ub.nframes * es;
+                    for (int c = 0; c < ub.nchannels; ++c) {
+                        char* r = cur + c * row;
+                        char* u = (char*)ub.ptr + (size_t)c * ub.ld * es;
+                        if (to_ring) pieces.push_back({r, u, row});
+                        else pieces.push_back({u, r, row});
+                    }
+                    cur += row * ub.nchannels;
+                }
+        };
         int k = 0;
         for (int64_t i0 = 0; i0 < ninst; i0 += wave, ++k) {
             const int s = k % kHostSlots;
@@ -1636,81 +1713,39 @@ void run_host_on_device(sigops_plan& p, int di, int64_t i_begin, int64_t i_end, 
             const int64_t w = std::min(wave, ninst - i0);
             finish(s);                  // the buffer's previous wave has left the device (and the pinned ring)
             slot.arena.reset();
-            din.assign((size_t)w * nin, sigops_buffer{});
-            dout.assign((size_t)w * nout, sigops_buffer{});
-            // device staging: buffer-major so that the same buffer of consecutive instances is contiguous; host
-            // runs that are contiguous too (one big batch array, or the pinned ring) become ONE copy
-            for (uint32_t b = 0; b < nin; ++b)
-                for (int64_t i = 0; i < w; ++i) {
-                    const sigops_buffer& hb = in[(i_begin + i0 + i) * nin + b];
-                    sigops_buffer& db = din[i * nin + b];
-                    db = hb;
-                    db.ld = round_up(std::max<int64_t>(hb.nframes, 1), 16);
-                    db.ptr = slot.arena.take_packed((size_t)db.ld * hb.nchannels * elem_size(hb.dtype));
-                }
-            for (uint32_t b = 0; b < nout; ++b)
-                for (int64_t i = 0; i < w; ++i) {
-                    const sigops_buffer& hb = out[(i_begin + i0 + i) * nout + b];
-                    sigops_buffer& db = dout[i * nout + b];
-                    db = hb;
-                    db.ld = round_up(std::max<int64_t>(hb.nframes, 1), 16);
-                    db.ptr = slot.arena.take_packed((size_t)db.ld * hb.nchannels * elem_size(hb.dtype));
-                }
+            stage_side(slot, in + (i_begin + i0) * nin, w, nin, 0, true, din, cin_u, cin_d, wav_in);
+            stage_side(slot, out + (i_begin + i0) * nout, w, nout, nin + p.h.n_temps, false, dout, cout_u, cout_d, wav_out);
             // ---- H2D on the copy-in stream
-            const sigops_buffer* src = in + (i_begin + i0) * nin;
+            const sigops_buffer* src = cin_u.data();
             if (!pinned_in && nin) {
-                // user arrays -> pinned ring (dense, buffer-major like the device staging), by worker threads
-                hin.assign((size_t)w * nin, sigops_buffer{});
-                std::vector<CopyPiece> pieces;
-                char* cur = dev.stage_in[s].base;
-                for (uint32_t b = 0; b < nin; ++b)
-                    for (int64_t i = 0; i < w; ++i) {
-                        const sigops_buffer& ub = src[i * nin + b];
-                        sigops_buffer& hb = hin[i * nin + b];
-                        hb = ub;
-                        hb.ld = ub.nframes;
-                        hb.ptr = cur;
-                        const size_t es = elem_size(ub.dtype), row = (size_t)ub.nframes * es;
-                        for (int c = 0; c < ub.nchannels; ++c)
-                            pieces.push_back({cur + c * row, (const char*)ub.ptr + (size_t)c * ub.ld * es, row});
-                        cur += row * ub.nchannels;
-                    }
+                std::vector<CopyPiece> pieces;                     // user arrays -> pinned ring, by worker threads
+                ring_views(dev.stage_in[s].base, cin_u, w, nin, hin, pieces, true);
                 parallel_copy(pieces, nthreads);
                 src = hin.data();
                 ++res.staged_waves;
             }
             CUDA_OK(cudaEventRecord(dev.ev_t[s][0], dev.s_in));
-            res.h2d += copy_runs(src, din.data(), w, nin, true, dev.s_in, !pinned_in);
+            res.h2d += copy_runs(src, cin_d.data(), w, nin, true, dev.s_in, !pinned_in);
             CUDA_OK(cudaEventRecord(dev.ev_t[s][1], dev.s_in));
             CUDA_OK(cudaEventRecord(dev.ev_in[s], dev.s_in));
-            // ---- stages on the slot's stream
+            // ---- stages on the slot's stream (WAV-layout inputs are transposed / decoded first, outputs encoded last)
             CUDA_OK(cudaStreamWaitEvent(slot.stream, dev.ev_in[s], 0));
+            for (auto& j : wav_in) launch_wav(false, j.P, slot.stream);
             WaveIO io{w, din.data(), dout.data()};
-            res.launches += enqueue_wave(p, di, slot, slot.stream, io);
+            res.launches += enqueue_wave(p, di, slot, slot.stream, io) + (int64_t)wav_in.size() + (int64_t)wav_out.size();
+            for (auto& j : wav_out) launch_wav(true, j.P, slot.stream);
+            CUDA_OK(cudaGetLastError());
             CUDA_OK(cudaEventRecord(dev.ev_k[s], slot.stream));
             // ---- D2H on the copy-out stream
             CUDA_OK(cudaStreamWaitEvent(dev.s_out, dev.ev_k[s], 0));
-            sigops_buffer* dst = out + (i_begin + i0) * nout;
+            const sigops_buffer* dst = cout_u.data();
             fl[s].drain.clear();
             if (!pinned_out) {
-                hout.assign((size_t)w * nout, sigops_buffer{});
-                char* cur = dev.stage_out[s].base;
-                for (uint32_t b = 0; b < nout; ++b)
-                    for (int64_t i = 0; i < w; ++i) {
-                        const sigops_buffer& ub = dst[i * nout + b];
-                        sigops_buffer& hb = hout[i * nout + b];
-                        hb = ub;
-                        hb.ld = ub.nframes;
-                        hb.ptr = cur;
-                        const size_t es = elem_size(ub.dtype), row = (size_t)ub.nframes * es;
-                        for (int c = 0; c < ub.nchannels; ++c)
-                            fl[s].drain.push_back({(char*)ub.ptr + (size_t)c * ub.ld * es, cur + c * row, row});
-                        cur += row * ub.nchannels;
-                    }
+                ring_views(dev.stage_out[s].base, cout_u, w, nout, hout, fl[s].drain, false);
                 dst = hout.data();
             }
             CUDA_OK(cudaEventRecord(dev.ev_t[s][2], dev.s_out));
-            res.d2h += copy_runs(dst, dout.data(), w, nout, false, dev.s_out, !pinned_out);
+            res.d2h += copy_runs(dst, cout_d.data(), w, nout, false, dev.s_out, !pinned_out);
             CUDA_OK(cudaEventRecord(dev.ev_t[s][3], dev.s_out));
             CUDA_OK(cudaEventRecord(dev.ev_out[s], dev.s_out));
             fl[s].i0 = i0; fl[s].w = w; fl[s].live = true;
@@ -1931,7 +1966,7 @@ int sigops_plan_run(sigops_plan* plan, int64_t ninst, const sigops_buffer* in, s
     if (!plan) return SIGOPS_ERR_INVALID;
     return guarded(plan->ctx, [&] {
         sigops_ctx* ctx = plan->ctx;
-        validate_io(*plan, ninst, in, out);
+        validate_io(*plan, ninst, in, out, true);
         std::unique_lock<std::mutex> lk(ctx->mu);
         auto t0 = std::chrono::steady_clock::now();
         const int nd = (int)ctx->devs.size();

@@ -3,7 +3,8 @@ from .dspjl import (Bandpass, Bandstop, Biquad, Butterworth, Chebyshev1, Highpas
                     Lowpass, PolynomialRatio, SecondOrderSections, ZeroPoleGain,
                     digitalfilter)
 from .functors import AffineCos, AffineSin, Sawtooth
-from .gpusink import Array, GPUSink, Tuple, sink, sink_batch, sink_into
+from .gpusink import Array, GPUSink, Tuple, sink, sink_batch, sink_into, sink_wav
+from .wav import WavFile, WavRaw, WavSignal, read_wav, write_wav
 from .graph import (AddChannel, After, Amplify, Append, Extend, FadeTo, Filt, Format, Functor,
                     Mix, Normpower, Operate, OperateOn, Pad, Prepend, Ramp, RampOff, RampOn,
                     SelectChannel, Signal, SignalError, ToChannels, ToEltype, ToFramerate,

@@ -195,6 +195,10 @@ class CompiledPlan:
         (the Julia layout); C-ordered input is copied by the caller beforehand."""
         bufs = (Buffer * len(arrays))()
         for k, a in enumerate(arrays):
+            if hasattr(a, "raw") and hasattr(a, "enc"):          # wav.WavRaw: frame-interleaved file layout
+                n, c = a.raw.shape
+                bufs[k] = Buffer(a.raw.ctypes.data, n, c, a.enc | 0x100, n)
+                continue
             n, c = (a.shape[0], 1) if a.ndim == 1 else a.shape
             if a.ndim == 2 and c > 1 and n > 0 and (a.strides[1] < n * a.itemsize or a.strides[1] % a.itemsize):
                 raise ValueError("multi-channel host buffers must be column-major (channels at least nframes apart)")

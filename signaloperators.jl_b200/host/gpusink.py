@@ -15,6 +15,7 @@ import numpy as np
 
 from . import cabi, graph as G
 from .lowering import Lowerer, np_dtype
+from .wav import WavRaw, write_wav
 from .lowering import dtype_code as dtype_code_of
 
 
@@ -77,6 +78,12 @@ def _wrap(plan, data, to):
 
 
 def _colmajor(a):
+    if isinstance(a, WavRaw):
+        return a
+    return _colmajor_array(a)
+
+
+def _colmajor_array(a):
     """Dense channel-planar view of `a` for the C ABI (element (n,c) at ptr[c*ld + n]): strided
     1-D / (N,1) views (`x[::2]`, `stereo[:,0]` of a C-ordered array, `x[::-1]`) and C-ordered
     matrices are copied; anything already dense in Julia's column-major layout is passed as is."""
@@ -114,6 +121,33 @@ def sink(x=None, to=None):
         cp = to.compiled(plan.tobytes())
         to.last_stats = cp.run_host(1, [_colmajor(a) for a in plan.input_arrays], [data])
     return _wrap(plan, data, to)
+
+
+def sink_wav(x, path, to, encoding=None):
+    """`sink(x, "file.wav")` (src/sink.jl:139-142 + src/WAV.jl:3-7) on the GPU sink: the root stage's output is
+    transposed to frame-interleaved order and converted to the file's sample encoding on the device
+    (csrc/k_wav.cuh), so the host only prepends the RIFF header.  `encoding`: "float64" (default for Float64
+    signals, what WAV.jl writes for a Float64 matrix), "float32" (default for Float32 signals) or "pcm16"
+    (round(clamp(x,-1,1)*32767)).  Returns the frame rate written, `round(Int, framerate(x))`."""
+    if not isinstance(to, GPUSink):
+        raise G.SignalError("sink_wav needs a GPUSink")
+    plan = Lowerer().build(x)
+    out = plan.outputs[0]
+    if np_dtype(out.dtype) not in (np.float32, np.float64):
+        raise G.SignalError("only floating-point signals are written as WAV by the GPU sink")
+    enc = encoding or ("float32" if np_dtype(out.dtype) == np.float32 else "float64")
+    dt = {"float64": np.float64, "float32": np.float32, "pcm16": np.int16}.get(enc)
+    if dt is None:
+        raise G.SignalError(f"unknown WAV encoding {enc!r}")
+    nbytes = out.nframes * out.nchannels * np.dtype(dt).itemsize
+    raw = (cabi.pinned_empty((out.nframes, out.nchannels), dt, order="C") if nbytes >= _PIN_MIN_BYTES
+           else np.empty((out.nframes, out.nchannels), dtype=dt))
+    if out.nframes > 0:
+        cp = to.compiled(plan.tobytes())
+        to.last_stats = cp.run_host(1, [_colmajor(a) for a in plan.input_arrays], [WavRaw(raw)])
+    fs = int(round(plan.framerate))
+    write_wav(path, raw, fs)
+    return fs
 
 
 def sink_into(result, x, to):

@@ -23,6 +23,7 @@ import numpy as np
 
 from . import dspjl, graph as G
 from .functors import functor_code
+from .wav import WavSignal
 
 # ---- constants mirrored from include/signalops.h -------------------------------
 F32, F64, I64 = 1, 2, 3
@@ -256,6 +257,17 @@ class Lowerer:
         self._keepalive.append(arr)
         return ("in", k)
 
+    def add_wav_input(self, wav):
+        key = id(wav)
+        if key in self._input_ids:
+            return ("in", self._input_ids[key])
+        k = len(self.plan.inputs)
+        self.plan.inputs.append(BufDesc(wav.shape[0], wav.shape[1], F64))
+        self.plan.input_arrays.append(wav)
+        self._input_ids[key] = k
+        self._keepalive.append(wav)
+        return ("in", k)
+
     def add_temp(self, nframes, nch, dtype):
         self.plan.temps.append(BufDesc(int(nframes), int(nch), dtype_code(dtype)))
         return ("tmp", len(self.plan.temps) - 1)
@@ -306,6 +318,11 @@ class Lowerer:
     def lower(self, x, shift, lo, hi, cm, co, clo, chi):
         if lo >= hi or clo >= chi:
             return []
+        if isinstance(x, WavSignal):
+            # samples still in file layout (frame-interleaved PCM16 / float): decoded on the device
+            tag = self.add_wav_input(x.wav)
+            return [Piece(lo, hi, clo, chi, [Instr(OP_LOAD, LEAF_BUF, buf=tag, c_mul=cm, c_off=co,
+                                                   i0=shift, i1=x.wav.shape[0])])]
         if isinstance(x, G.ArraySignal):
             tag = self.add_input(x.data)
             n = x.data.shape[0]

@@ -126,6 +126,40 @@ function SignalOperators.sink(xs::AbstractVector, to::GPUSink)
     [initsink(x, refineroot(root(x)), r) for (x, r) in zip(xs, results)]
 end
 
+# `sink(x, "file.wav")` (src/sink.jl:139-142, src/WAV.jl:3-7) on the GPU sink: the device transposes the result to
+# frame-interleaved order (a C x N column-major Julia matrix IS a WAV data chunk) and converts the samples
+# (Float64 / Float32 / PCM16), so the host only writes the RIFF header in front of the bytes.
+const SIGOPS_INTERLEAVED = Int32(0x100)
+function SignalOperators.sink(x, to::GPUSink, filename::String; encoding::Type = sampletype(x) === Float32 ? Float32 : Float64)
+    x = process_sink_params(x)
+    plan = lower(x)
+    n, c = nframes(x), nchannels(x)
+    raw = Array{encoding,2}(undef, c, n)
+    enc = encoding === Int16 ? Int32(4) : dtypecode(encoding)
+    if n > 0
+        handle = compiled(to, plan.bytes)
+        ins = [buffer(a) for a in plan.inputs]
+        outs = [SigopsBuffer(pointer(raw), n, c, enc | SIGOPS_INTERLEAVED, n)]
+        stats = SigopsStats()
+        GC.@preserve plan raw check(to, ccall((:sigops_plan_run, libsignalops), Cint,
+            (Ptr{Cvoid}, Int64, Ptr{SigopsBuffer}, Ptr{SigopsBuffer}, Ref{SigopsStats}), handle, 1, ins, outs, stats))
+    end
+    fs = round(Int, framerate(x))                                 # src/WAV.jl:5
+    isfloat = encoding <: AbstractFloat
+    open(filename, "w") do io
+        fmt = IOBuffer()
+        foreach(v -> write(fmt, htol(v)), (UInt16(isfloat ? 3 : 1), UInt16(c), UInt32(fs), UInt32(fs * c * sizeof(encoding)),
+                                          UInt16(c * sizeof(encoding)), UInt16(8 * sizeof(encoding))))
+        isfloat && write(fmt, htol(UInt16(0)))
+        fmtb = take!(fmt)
+        fact = isfloat ? vcat(Vector{UInt8}("fact"), reinterpret(UInt8, [htol(UInt32(4)), htol(UInt32(n))])) : UInt8[]
+        nbytes = sizeof(raw)
+        write(io, "RIFF", htol(UInt32(4 + 8 + length(fmtb) + length(fact) + 8 + nbytes)), "WAVE", "fmt ", htol(UInt32(length(fmtb))), fmtb,
+              fact, "data", htol(UInt32(nbytes)), raw)
+    end
+    fs
+end
+
 dtypecode(::Type{Float32}) = Int32(1)
 dtypecode(::Type{Float64}) = Int32(2)
 dtypecode(::Type{<:Integer}) = Int32(3)
