@@ -393,21 +393,48 @@ def _resolve_filter(x):
     if isinstance(h, host_dspjl.Biquad):
         return np.array([h.astuple()]), 1.0
     if isinstance(h, host_dspjl.PolynomialRatio):
+        if len(h.b) > 3 or len(h.a) > 3:
+            # DSP.jl runs the order-n DF2T recurrence with an (n-1)... state vector: that is
+            # scipy.signal.lfilter's structure; the state is carried between blocks
+            return DirectForm(h.b, h.a)
         b = list(h.b) + [0.0] * (3 - len(h.b))
         a = list(h.a) + [0.0] * (3 - len(h.a))
-        if len(b) > 3 or len(a) > 3:
-            raise NotImplementedError("oracle: PolynomialRatio above order 2")
         return np.array([[b[0], b[1], b[2], a[1], a[2]]]), 1.0
+    if isinstance(h, host_dspjl.FIRFilter) and h.kind == "standard":
+        return D.StandardFIR(h.h)
     raise TypeError(f"oracle cannot resolve filter {h!r}")
+
+
+class DirectForm:
+    """Order-n transposed direct form II with streaming state (DSP.jl `DF2TFilter(::PolynomialRatio)`)."""
+
+    def __init__(self, b, a):
+        from scipy import signal as sps
+        n = max(len(b), len(a))
+        self.b = np.concatenate([np.asarray(b, dtype=np.float64), np.zeros(n - len(b))])
+        self.a = np.concatenate([np.asarray(a, dtype=np.float64), np.zeros(n - len(a))])
+        self.zi = np.zeros(n - 1)
+        self._lfilter = sps.lfilter
+
+    rate = 1.0
+
+    def outputlength(self, n):
+        return n
+
+    def filt(self, x):
+        y, self.zi = self._lfilter(self.b, self.a, x, zi=self.zi)
+        return y
 
 
 def _filter_init(x):
     C = x.signal.nchannels
     hs = [_resolve_filter(x) for _ in range(C)]          # src/filters.jl:205 (one per channel)
-    resamp = isinstance(hs[0], D.Resampler)
+    resamp = isinstance(hs[0], (D.Resampler, D.StandardFIR, DirectForm))
     N = x.nframes
     bs = x.blocksize
-    if resamp:                                           # init_length, src/filters.jl:185-199
+    if resamp and not isinstance(x.fn, G.ResamplerFn):   # single-rate streaming objects: plain blocks
+        inlen = bs if _inf(N) else min(N, bs)
+    elif resamp:                                         # init_length, src/filters.jl:185-199
         ratio = float(x.fn.ratio)
         n = int(max(1, (bs if _inf(N) else min(N, bs)) / ratio))
         if hs[0].outputlength(n) <= 0:

@@ -173,6 +173,40 @@ def taps2pfb(h, nphi):
     return pfb
 
 
+class StandardFIR:
+    """FIRFilter(h) with ratio 1 (DSP.jl FIRStandard, App. B.4): y[n] = sum_k h[k] x[n-k], history carried
+    between calls, no phase shift."""
+
+    def __init__(self, h):
+        h = np.asarray(h, dtype=np.float64)
+        st = FirState()
+        st.kind = 0
+        st.h_len = len(h)
+        st.n_phi, st.taps_per_phi = 1, len(h)
+        st.interpolation = st.decimation = 1
+        st.input_deficit = 1
+        st.phi_idx = 1
+        st.x_idx = 1
+        st.rate = 1.0
+        self._pfb = np.asfortranarray(h[::-1].reshape(-1, 1))
+        self._hist = np.zeros(max(1, len(h) - 1), dtype=np.float64)
+        st.pfb = _dp(self._pfb)
+        st.dpfb = _dp(self._pfb)
+        st.history = _dp(self._hist)
+        self.st = st
+
+    rate = 1.0
+
+    def outputlength(self, n):
+        return max(0, n - self.st.input_deficit + 1)
+
+    def filt(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        buf = np.empty(len(x) + 64, dtype=np.float64)
+        n = lib().oracle_fir_filt(_dp(buf), len(buf), C.byref(self.st), _dp(x), len(x))
+        return buf[:n]
+
+
 class Resampler:
     """FIRFilter(resample_filter(ratio), ratio) + setphase!(timedelay) — the object
     `ResamplerFn(fs)` returns at src/reformatting.jl:92-99 — as streaming state."""

@@ -9,7 +9,7 @@ from .graph import (AddChannel, After, Amplify, Append, Extend, FadeTo, Filt, Fo
                     Mix, Normpower, Operate, OperateOn, Pad, Prepend, Ramp, RampOff, RampOn,
                     SelectChannel, Signal, SignalError, ToChannels, ToEltype, ToFramerate,
                     Uniform, Until, Window, cos, cycle, duration, framerate, identity, inflen,
-                    lastframe, mirror, nchannels, nframes, one, randn, sampletype, sin,
+                    lastframe, mirror, nchannels, nframes, one, randn, reverse, sampletype, sin,
                     sinramp, zero)
 from .lowering import LoweringError
 from .units import Hz, dB, deg, frames, kframes, kHz, ms, rad, s

@@ -345,12 +345,28 @@ def to_sos(h):
     if isinstance(h, Biquad):
         return SecondOrderSections([h], 1.0)
     if isinstance(h, PolynomialRatio):
-        if len(h.a) > 3 or len(h.b) > 3:
-            raise NotImplementedError(
-                "PolynomialRatio filters above order 2 are not lowered to the GPU path yet")
-        b = list(h.b) + [0.0] * (3 - len(h.b))
-        a = list(h.a) + [0.0] * (3 - len(h.a))
-        return SecondOrderSections([Biquad(b[0], b[1], b[2], a[1], a[2])], 1.0)
+        if len(h.a) <= 3 and len(h.b) <= 3:
+            b = list(h.b) + [0.0] * (3 - len(h.b))
+            a = list(h.a) + [0.0] * (3 - len(h.a))
+            return SecondOrderSections([Biquad(b[0], b[1], b[2], a[1], a[2])], 1.0)
+        # order n: DSP.jl runs the order-n DF2T recurrence (src/filters.jl:89-95, App. B.2).  The device runs
+        # biquad cascades, so the ratio is factored (roots of numerator and denominator -> zero-pole-gain ->
+        # the same pairing as `convert(SecondOrderSections, ::ZeroPoleGain)`): the same transfer function,
+        # equal to the direct form up to rounding (and better conditioned for high orders).
+        b = np.trim_zeros(np.asarray(h.b, dtype=np.float64), "f")
+        lead = len(h.b) - len(b)                       # leading zeros of b: pure delays z^-lead
+        if len(b) == 0:
+            return SecondOrderSections([Biquad(0.0, 0.0, 0.0, 0.0, 0.0)], 1.0)
+        # H = b[0] * prod(1 - z_i z^-1) / prod(1 - p_i z^-1) * z^-lead; roots at the origin are factors of 1, so the
+        # two lists are padded with them to equal length (no delay is introduced by that)
+        z = list(np.roots(b))
+        pz = list(np.roots(np.asarray(h.a, dtype=np.float64)))
+        n = max(len(z), len(pz))
+        z += [0.0] * (n - len(z))
+        pz += [0.0] * (n - len(pz))
+        sos = zpk_to_sos(ZeroPoleGain(z, pz, float(b[0]))) if n else SecondOrderSections([], float(b[0]))
+        delays = [Biquad(0.0, 0.0, 1.0, 0.0, 0.0)] * (lead // 2) + [Biquad(0.0, 1.0, 0.0, 0.0, 0.0)] * (lead % 2)
+        return SecondOrderSections(list(sos.biquads) + delays, sos.g)
     raise TypeError(f"not a filter coefficient object: {h!r}")
 
 

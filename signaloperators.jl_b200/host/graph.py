@@ -695,6 +695,12 @@ class TupleCat:
 
 tuplecat = TupleCat()
 
+
+def reverse(frame):
+    """Julia's `reverse` on a frame tuple: `OperateOn(reverse, x, bychannel=false)` swaps the channel order
+    (test/runtests.jl:273-276).  One of the enumerated whole-frame functions the GPU sink lowers."""
+    return tuple(reversed(frame))
+
 _ARITH = {operator.add: "+", operator.mul: "*", operator.sub: "-", operator.truediv: "/",
           operator.neg: "neg", "+": "+", "*": "*", "-": "-", "/": "/"}
 

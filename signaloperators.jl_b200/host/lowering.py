@@ -625,8 +625,15 @@ class Lowerer:
             st.interpolation, st.decimation = 1, f.decimation
             st.pfb_table = self.add_table(f.hrev.reshape(1, -1))
             st.phase0 = 1.0
+        elif f.kind == "standard":
+            # single-rate FIR (`Filt(x, FIRFilter(h))`, DSP.jl FIRStandard): the decimator kernel with step 1
+            st.fir_kind = FIR_DECIMATOR
+            st.n_phases, st.taps_per_phase = 1, f.hlen
+            st.interpolation, st.decimation = 1, 1
+            st.pfb_table = self.add_table(f.hrev.reshape(1, -1))
+            st.phase0 = 1.0
         else:
-            raise LoweringError("single-rate FIR filters are not lowered to the GPU path yet")
+            raise LoweringError(f"FIR kernel kind {f.kind!r} is not lowered to the GPU path")
         self.plan.stages.append(st)
         if f32:
             tag32 = self.add_temp(n_out, C, T)
@@ -711,8 +718,16 @@ class Lowerer:
                         out += self.lower(k, shift, lo, hi, 1, co - off, a, b)
                 off += kc
             return out
+        if fn is G.reverse and len(kids) == 1:
+            # channel c of the result is channel C-1-c of the child: one piece per channel
+            C = kids[0].nchannels
+            out = []
+            for c in range(clo, chi):
+                src = c * cm + co if cm else co
+                out += self.lower(kids[0], shift, lo, hi, 0, C - 1 - src, c, c + 1)
+            return out
         raise LoweringError("whole-frame OperateOn functions other than ToChannels/AddChannel/"
-                            "SelectChannel are not lowered to the GPU sink")
+                            "SelectChannel/reverse are not lowered to the GPU sink")
 
     # ---- post passes -----------------------------------------------------------------------
     def _fuse_epilogues(self):

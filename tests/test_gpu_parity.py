@@ -377,7 +377,48 @@ def test_raw_filter_objects(gpu):
     h = digitalfilter(Highpass(8, fs=100), Chebyshev1(5, 1))
     a = check(gpu, lambda: Signal(x, 100 * Hz) >> Filt(h))
     b = check(gpu, lambda: Signal(x, 100 * Hz) >> Filt(Highpass, 8 * Hz, method=Chebyshev1(5, 1)))
-    assert np.max(np.abs(a[0] - b[0])) <= 1e-12 * rms(b[0])                           # runtests.jl:364-368
+    assert np.max(np.abs(a - b)) <= 1e-12 * rms(b)                                    # runtests.jl:364-368
     check(gpu, lambda: Signal(x, 100 * Hz) >> Filt(digitalfilter(Lowpass(20, fs=100), Butterworth(4))))
     check(gpu, lambda: Signal(x, 100 * Hz) >> Filt(Biquad(0.2, 0.3, 0.1, -0.5, 0.25)))
     check(gpu, lambda: Signal(x, 100 * Hz) >> Filt(PolynomialRatio([0.3, 0.2], [1.0, -0.4, 0.1])))
+
+
+# ---- operator leftovers: order-n PolynomialRatio, single-rate FIR, whole-frame `reverse` ----
+
+def test_polynomial_ratio_of_any_order(gpu):
+    """src/filters.jl:65,89-95: `Filt(x, PolynomialRatio(b, a))` runs DSP.jl's order-n DF2T recurrence; the GPU
+    runs the same transfer function factored into biquads (oracle: scipy.signal.lfilter, the direct form)."""
+    from scipy import signal as sps
+    from signalops import PolynomialRatio
+    x = rng(41).standard_normal((6000, 2))
+    for b, a in (sps.butter(5, 0.3), sps.cheby1(7, 1, 0.2), ([0.0, 0.5, 0.2, 0.1], [1, -0.3, 0.2, 0.05, 0.01]),
+                 ([1, 0.4, 0.3, 0.2, 0.1, 0.05], [1.0, -0.2])):
+        got = check(gpu, lambda: Signal(x, 100 * Hz) >> Filt(PolynomialRatio(b, a)), tol=1e-9)
+        ref = np.stack([sps.lfilter(b, a, x[:, c]) for c in range(2)], axis=1)
+        assert np.max(np.abs(got - ref)) <= 1e-9 * rms(ref)
+
+
+def test_single_rate_fir_filter(gpu):
+    """`Filt(x, FIRFilter(h))` (DSP.jl FIRStandard through src/filters.jl:240-262): every FIR kernel of the library."""
+    from scipy import signal as sps
+    from signalops import dspjl
+    h = sps.firwin(31, 0.3)
+    x = rng(42).standard_normal((7001, 2))
+    got = check(gpu, lambda: Signal(x, 100 * Hz) >> Filt(dspjl.FIRFilter(h, 1)) >> Amplify(-6 * dB))
+    ref = np.stack([sps.lfilter(h, 1.0, x[:, c]) for c in range(2)], axis=1) * 10 ** (-6 / 20)
+    assert got.shape == (7001, 2) and np.max(np.abs(got - ref)) <= 1e-12 * rms(ref)
+    xs = [rng(43 + k).standard_normal((5000, 2)) for k in range(40)]          # 80 rows: the tensor-map kernel
+    outs = sink_batch([Signal(v, 100 * Hz) >> Filt(dspjl.FIRFilter(h, 1)) for v in xs], gpu)
+    for k in (0, 39):
+        ref = np.stack([sps.lfilter(h, 1.0, xs[k][:, c]) for c in range(2)], axis=1)
+        assert np.max(np.abs(outs[k][0] - ref)) <= 1e-12 * rms(ref)
+
+
+def test_whole_frame_reverse(gpu):
+    """test/runtests.jl:273-276: `OperateOn(reverse, x, bychannel=false)` swaps the channels."""
+    from signalops import reverse
+    x = rng(44).random((20, 2))
+    got = sink(OperateOn(reverse, x, bychannel=False) >> ToFramerate(20 * Hz), gpu)
+    assert np.array_equal(got[0], np.stack([x[:, 1], x[:, 0]], axis=1))
+    y = rng(45).random((50, 5))
+    check(gpu, lambda: OperateOn(reverse, Signal(y, 10 * Hz), bychannel=False) >> Amplify(2), exact=True)
