@@ -515,6 +515,29 @@ def run_gpu(args, rank, world, local_rank):
     e2e_value = world * e2e_ninst * N_OUT * NCH * e2e_steps / sec_pin / 1e6
     e2e_pg_value = world * pg_ninst * N_OUT * NCH * 2 / sec_pg / 1e6
 
+    # ---- the call a user makes: sink(list of graphs, GPUSink) — lowering of every graph in Python, page-locked
+    # result arrays (pooled after the first call), sigops_plan_run on pageable inputs
+    api = None
+    if rank == 0:
+        from signalops import GPUSink, sink_batch
+        napi = 32
+        gsink = GPUSink([local_rank])
+        xs_api = [np.asfortranarray(batch.xs[0][i].cpu().numpy().T) for i in range(napi)]
+        res_api = sink_batch([graph_cfg3(x) for x in xs_api], gsink)       # first call: plan creation, staging ring
+        t0 = time.perf_counter()
+        nrep = 3
+        for _ in range(nrep):
+            del res_api
+            res_api = sink_batch([graph_cfg3(x) for x in xs_api], gsink)
+        sec_api = (time.perf_counter() - t0) / nrep
+        api_err = float(np.max(np.abs(res_api[0][0].T - ref0.numpy())) / float(ref0.pow(2).mean().sqrt()))
+        api = {"value": napi * N_OUT * NCH / sec_api / 1e6, "unit": "Msamples/s", "instances_per_call": napi,
+               "ms_per_call": sec_api * 1e3, "matches_device_run": bool(api_err < 1e-9),
+               "what": "sink([ToFramerate(Signal(x,44.1kHz),48kHz) for x in xs], GPUSink()): graph construction, lowering of "
+                       "every graph (Python mirror), pageable numpy inputs and results (first-touch page faults of the fresh result arrays included)"}
+        del res_api, xs_api
+        gsink.close()
+
     peak, peak_src = measured_peaks()
     fir_ms, fir_n = prof.get("fir", (0.0, 0))
     alg_bytes = FIR_BYTES_PER_OUT * samples_step
@@ -569,9 +592,10 @@ def run_gpu(args, rank, world, local_rank):
                     "pageable": {"value": e2e_pg_value, "unit": "Msamples/s", "instances_per_step": pg_ninst,
                                  "ms_per_step": sec_pg / 2 * 1e3, "matches_device_run": bool(pg_err < 1e-9),
                                  "note": "caller arrays not page-locked (what a Julia Array is): staged through the "
-                                         "library's pinned ring"}},
+                                         "library's pinned ring"},
+                    "public_api": api},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_fir_mma (FP64 tensor-core polyphase FIR, TMA ring)",
+            "roofline": {"bound": "hbm", "kernel": "k_fir_tmap (FP64 tensor-core polyphase FIR: DMMA.8x8x4, tensor-map TMA ring and stores)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
                          "traffic": ncu_traffic("k_fir_mma_traffic_bytes_per_out_sample") and

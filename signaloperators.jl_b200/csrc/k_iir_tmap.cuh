@@ -68,7 +68,7 @@ struct IirTmapParams {
     int64_t N, L, Wc;          // frames, chunk length, warm-up (both multiples of the stage)
     int64_t cpr;               // chunks per row
     int64_t nunits;            // row groups * cpr
-    double gain, scale;
+    double gain, scale, scale2;     // y = ((cascade * gain) * scale) * scale2: the epilogue's constants, applied in order
     double coef[kIirMaxSections][5];
     // Fused elementwise programs whose leaves do not depend on the row (constants, generators, ramps — e.g.
     // BASELINE config 5: x * (0.5 sin + 0.5) before the cascade, y * ramp_on * ramp_off + tone after it):
@@ -118,8 +118,8 @@ __device__ __forceinline__ void apply_leaf16(int op, double* acc, const double* 
 }
 
 template <int M, bool UNITB, class T, bool LV = false>
-__device__ __forceinline__ double cascade16_swz(Cascade<M>& f, unsigned char* row, int key, int blk, double gain, double sc, int nvalid,
-                                                const IirTmapParams* P = nullptr, const double* lv = nullptr, int lvpitch = 0) {
+__device__ __forceinline__ double cascade16_swz(Cascade<M>& f, unsigned char* row, int key, int blk, double gain, double sc, double sc2,
+                                                int nvalid, const IirTmapParams* P = nullptr, const double* lv = nullptr, int lvpitch = 0) {
     double xr[16];
     if (sizeof(T) == 8) {
 #pragma unroll
@@ -146,7 +146,7 @@ __device__ __forceinline__ double cascade16_swz(Cascade<M>& f, unsigned char* ro
             if (k >= 0 && k < 16) {
                 const double in = (j == 0) ? xr[k] : pipe[j - 1];
                 pipe[j] = biquad_step<M, UNITB>(f, j, in);
-                if (j == M - 1) out[k] = (pipe[j] * gain) * sc;
+                if (j == M - 1) out[k] = ((pipe[j] * gain) * sc) * sc2;
             }
         }
     }
@@ -273,7 +273,7 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
 #pragma unroll
             for (int blk = 0; blk < SUB / 16; ++blk) {
                 const int64_t rem = work - off - s * SUB - blk * 16;   // outputs of this block that exist
-                s3 += cascade16_swz<M, UNITB, T, LV>(f, rowp + s * 128, (SUBS * lane + s) & 7, blk, P.gain, P.scale,
+                s3 += cascade16_swz<M, UNITB, T, LV>(f, rowp + s * 128, (SUBS * lane + s) & 7, blk, P.gain, P.scale, P.scale2,
                                                      rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0), &P, lvbuf + s * SUB + blk * 16, SC);
             }
             if (s == 0 && h + NS - 1 < nstage) {

@@ -1054,9 +1054,10 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                         T.cpr = (N + bestL - 1) / bestL;
                         T.nunits = groups * T.cpr;
                         T.gain = g.gain;
-                        T.scale = s.iir.scale[0] * s.iir.scale[1];
+                        T.scale = s.iir.scale[0];          // (applied one after the other, like the reference's nested maps)
+                        T.scale2 = s.iir.scale[1];
                         if (rowinv) {
-                            T.scale = 1.0;
+                            T.scale = T.scale2 = 1.0;
                             T.n_in_ops = (int)s.iir.rv_in.size();
                             T.n_ep_ops = (int)s.iir.rv_ep.size();
                             for (int j = 0; j < T.n_in_ops; ++j) T.ops[j] = s.iir.rv_in[j];

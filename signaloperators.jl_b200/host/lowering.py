@@ -525,6 +525,8 @@ class Lowerer:
         tag, slot = memo
         prog = [Instr(OP_LOAD, LEAF_BUF, buf=tag, c_mul=cm, c_off=co, i0=shift, i1=N),
                 Instr(OP_DIV, LEAF_RMS, buf=slot, d0=float(N * C))]
+        if np.dtype(x.sampletype) == np.float32:
+            prog.append(Instr(op=OP_CAST_F32))       # `vals ./= rms` is stored as Float32 before anything reads it
         return [Piece(lo, hi, clo, chi, prog)]
 
     def _materialize_filter(self, x, need):

@@ -48,13 +48,14 @@ mutable struct GPUSink
     devices::Vector{Cint}
     ctx::Ptr{Cvoid}
     plans::Dict{Vector{UInt8},Ptr{Cvoid}}
-    function GPUSink(devices = [0])
+    pin_results::Bool       # page-lock the arrays `sink` returns (0.6 s per GB: only for sinks that recycle results)
+    function GPUSink(devices = [0]; pin_results = false)
         ctx = Ref{Ptr{Cvoid}}(C_NULL)
         devs = Cint.(devices)
         rc = ccall((:sigops_ctx_create, libsignalops), Cint, (Ptr{Cint}, Cint, Ref{Ptr{Cvoid}}),
                    devs, length(devs), ctx)
         rc == 0 || error(lasterror(C_NULL))
-        s = new(devs, ctx[], Dict{Vector{UInt8},Ptr{Cvoid}}())
+        s = new(devs, ctx[], Dict{Vector{UInt8},Ptr{Cvoid}}(), pin_results)
         finalizer(s) do s
             foreach(p -> ccall((:sigops_plan_destroy, libsignalops), Cvoid, (Ptr{Cvoid},), p), values(s.plans))
             ccall((:sigops_ctx_destroy, libsignalops), Cvoid, (Ptr{Cvoid},), s.ctx)
@@ -73,11 +74,13 @@ function compiled(to::GPUSink, bytes::Vector{UInt8})
     end
 end
 
-# Page-locked result arrays: the sink allocates what it returns (`initsink`, src/sink.jl:115-121), so the
-# result can live where the device writes directly (include/signalops.h `sigops_host_alloc`).  Caller
-# arrays (inputs, `sink!` results) are ordinary pageable Julia arrays; the library stages those itself.
-function pinned_matrix(::Type{T}, n, c) where T
-    n * c * sizeof(T) < (1 << 20) && return Array{T,2}(undef, n, c)
+# Page-locked result arrays (opt-in, `GPUSink(pin_results = true)`): the sink allocates what it returns (`initsink`,
+# src/sink.jl:115-121), so the result can live where the device writes directly (include/signalops.h
+# `sigops_host_alloc`).  Page-locking costs ~0.6 s per GB, so this only pays for sinks whose results are recycled
+# (a pool behind the finalizer is the natural next step; host/cabi.py has one).  Caller arrays (inputs, `sink!`
+# results) and default results are ordinary pageable Julia arrays; the library stages those through its own pinned ring.
+function pinned_matrix(to::GPUSink, ::Type{T}, n, c) where T
+    (!to.pin_results || n * c * sizeof(T) < (1 << 20)) && return Array{T,2}(undef, n, c)
     p = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:sigops_host_alloc, libsignalops), Cint, (Csize_t, Ref{Ptr{Cvoid}}), n * c * sizeof(T), p)
     rc == 0 || error(lasterror(C_NULL))
@@ -93,7 +96,7 @@ SignalOperators.sink(to::GPUSink) = x -> sink(x, to)
 function SignalOperators.sink(x, to::GPUSink)
     x = process_sink_params(x)                                   # src/sink.jl:94-99
     plan = lower(x)                                              # graph -> stages (below)
-    result = pinned_matrix(plan.outtype, nframes(x), nchannels(x))   # initsink, src/sink.jl:115-117
+    result = pinned_matrix(to, plan.outtype, nframes(x), nchannels(x))   # initsink, src/sink.jl:115-117
     nframes(x) > 0 && run!(to, [plan], [result])
     initsink(x, refineroot(root(x)), result)
 end
@@ -121,7 +124,7 @@ function SignalOperators.sink(xs::AbstractVector, to::GPUSink)
     xs = process_sink_params.(xs)
     plans = lower.(xs)
     all(p -> p.bytes == plans[1].bytes, plans) || error("batch elements do not lower to the same plan")
-    results = [pinned_matrix(p.outtype, nframes(x), nchannels(x)) for (x, p) in zip(xs, plans)]
+    results = [pinned_matrix(to, p.outtype, nframes(x), nchannels(x)) for (x, p) in zip(xs, plans)]
     (isempty(xs) || nframes(xs[1]) == 0) || run!(to, plans, results)
     [initsink(x, refineroot(root(x)), r) for (x, r) in zip(xs, results)]
 end
@@ -482,8 +485,10 @@ function lower_node(lw, x::NormedSignal, shift, lo, hi, cm, co, clo, chi)       
         lw.memo[key] = (tag, slot)
     end
     tag, slot = lw.memo[key]
-    [Piece(lo, hi, clo, chi, [Instr(OP_LOAD, LEAF_BUF; buf = tag, c_mul = cm, c_off = co, i0 = shift, i1 = N),
-                              Instr(OP_DIV, LEAF_RMS; buf = slot, d0 = Float64(N * C))])]
+    prog = [Instr(OP_LOAD, LEAF_BUF; buf = tag, c_mul = cm, c_off = co, i0 = shift, i1 = N),
+            Instr(OP_DIV, LEAF_RMS; buf = slot, d0 = Float64(N * C))]
+    sampletype(x) === Float32 && push!(prog, Instr(OP_CAST_F32))      # `vals ./= rms` is stored as Float32
+    [Piece(lo, hi, clo, chi, prog)]
 end
 
 function lower_node(lw, x::FilteredSignal, shift, lo, hi, cm, co, clo, chi)            # src/filters.jl:204-262

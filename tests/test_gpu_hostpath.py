@@ -83,14 +83,21 @@ def test_strided_channels_through_the_staging_ring(gpu):
     assert np.all(outbig[24000:] == 7.0)
 
 
-def test_sink_returns_page_locked_results(gpu):
-    x = np.random.default_rng(3).standard_normal((300000, 2))
-    y, fs = sink(chain(x), gpu)
-    lib = C.CDLL("libcudart.so") if False else None     # (no cudart handle needed: the library tells us)
-    assert y.flags.f_contiguous and y.shape == (300000, 2)
-    want, _ = oracle.sink(chain(x))
-    assert np.max(np.abs(y - want)) <= TOL * rms(want)
-    del lib
+def test_sink_can_return_page_locked_results():
+    """GPUSink(pin_results=True): results live in sigops_host_alloc memory, recycled through a pool."""
+    pinned = GPUSink([0], pin_results=True)
+    try:
+        x = np.random.default_rng(3).standard_normal((300000, 2))
+        y, fs = sink(chain(x), pinned)
+        assert y.flags.f_contiguous and y.shape == (300000, 2)
+        want, _ = oracle.sink(chain(x))
+        assert np.max(np.abs(y - want)) <= TOL * rms(want)
+        addr = y.ctypes.data
+        del y
+        y2, _ = sink(chain(x), pinned)                  # the block comes back from the pool
+        assert y2.ctypes.data == addr and np.max(np.abs(y2 - want)) <= TOL * rms(want)
+    finally:
+        pinned.close()
 
 
 def test_replay_as_cuda_graph_matches_eager(gpu):
