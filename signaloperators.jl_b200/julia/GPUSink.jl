@@ -93,12 +93,28 @@ end
 # Same shape as `sink(x,to::String)` (src/sink.jl:139-142): validate, hand to the backend,
 # wrap like `initsink(x,T,data)` (src/sink.jl:120-121).
 SignalOperators.sink(to::GPUSink) = x -> sink(x, to)
-function SignalOperators.sink(x, to::GPUSink)
+function SignalOperators.sink(x, to::GPUSink; as = nothing)
     x = process_sink_params(x)                                   # src/sink.jl:94-99
     plan = lower(x)                                              # graph -> stages (below)
     result = pinned_matrix(to, plan.outtype, nframes(x), nchannels(x))   # initsink, src/sink.jl:115-117
     nframes(x) > 0 && run!(to, [plan], [result])
-    initsink(x, refineroot(root(x)), result)
+    wrapresult(x, as === nothing ? refineroot(root(x)) : as, result)
+end
+SignalOperators.sink(x, ::Type{T}, to::GPUSink) where T = sink(x, to; as = T)    # `sink(x, AxisArray)` etc.
+
+# `initsink(x,T,data)` exists for Array and Tuple (src/sink.jl:120-121).  Container sinks — AxisArray
+# (src/AxisArrays.jl:41-46), DimensionalArray (src/DimensionalData.jl:36-42), SampleBuf (src/SampledSignals.jl:17-18) —
+# only define the allocating `initsink(x,T)`: build the container with the reference's own method and fill it.
+# Sample types the device does not compute in (`Fixed{Int16,15}`, src/FixedPointNumbers.jl) are computed in
+# Float64 and converted on the way into the container, as `sink!` does per frame (src/sink.jl:262-267).
+function wrapresult(x, ::Type{T}, data) where T
+    if T <: Union{Array,Tuple} && eltype(data) === sampletype(x)
+        return initsink(x, T, data)
+    end
+    out = initsink(x, T)
+    dest = out isa Tuple ? out[1] : out
+    dest .= data
+    out
 end
 
 # `sink!(result, x)` semantics of src/sink.jl:158-168: a prefix of x, forced channel count.
@@ -126,7 +142,7 @@ function SignalOperators.sink(xs::AbstractVector, to::GPUSink)
     all(p -> p.bytes == plans[1].bytes, plans) || error("batch elements do not lower to the same plan")
     results = [pinned_matrix(to, p.outtype, nframes(x), nchannels(x)) for (x, p) in zip(xs, plans)]
     (isempty(xs) || nframes(xs[1]) == 0) || run!(to, plans, results)
-    [initsink(x, refineroot(root(x)), r) for (x, r) in zip(xs, results)]
+    [wrapresult(x, refineroot(root(x)), r) for (x, r) in zip(xs, results)]
 end
 
 # `sink(x, "file.wav")` (src/sink.jl:139-142, src/WAV.jl:3-7) on the GPU sink: the device transposes the result to
@@ -335,7 +351,8 @@ end
 function lower(x; nframes = SignalOperators.nframes(x), outtype = nothing)
     lw = Lowerer()
     N, C = Int(nframes), nchannels(x)
-    T = outtype === nothing ? (sampletype(x) <: Union{Integer,Bool} ? Int64 : sampletype(x)) : outtype
+    S = sampletype(x)
+    T = outtype !== nothing ? outtype : S <: Union{Integer,Bool} ? Int64 : S <: Union{Float32,Float64} ? S : Float64
     push!(lw.outputs, BufDesc(N, C, dtypecode(T)))
     pieces = N > 0 ? lower_node(lw, x, 0, 0, N, 1, 0, 0, C) : Piece[]
     push!(lw.stages, Stage(kind = STAGE_MAP, out_buf = (:out, 0), pieces = pieces, nchannels = C, n_out = N))
