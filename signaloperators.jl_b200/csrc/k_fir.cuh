@@ -130,6 +130,9 @@ k_fir(const __grid_constant__ FirParams P) {
     }
     // positions [jlo, jhi) of the tile exist in the signal; the rest is zero padding / history
     const int ncopy = npos + 1;
+    // the 16-byte copies below move position PAIRS: they own cells [0, ncopy_e); the zeroed slack starts after them
+    // (racecheck: the slack used to start at `ncopy` and overlap the last pair of an odd-length window)
+    const int ncopy_e = (ncopy + 1) & ~1;
     const int jlo = p0 < 0 ? (int)(-p0 < ncopy ? -p0 : ncopy) : 0;
     const int64_t avail = P.in_len - p0;
     const int jhi = avail < 0 ? 0 : (avail < ncopy ? (int)avail : ncopy);
@@ -152,7 +155,7 @@ k_fir(const __grid_constant__ FirParams P) {
                         cp_async16(dst + j, src + (nb ? j : jlo), nb);
                 }
             } else {
-                for (int j = lane; j < ncopy; j += 32) {
+                for (int j = lane; j < ncopy_e; j += 32) {
                     const bool ok = j >= jlo && j < jhi;
                     cp_async8(dst + j, src + (ok ? j : jlo), ok);
                 }
@@ -162,13 +165,13 @@ k_fir(const __grid_constant__ FirParams P) {
             const int64_t inst = row / P.nch;
             const int c = (int)(row - inst * P.nch);
             const BufRef ib = P.bufrefs[(size_t)inst * P.nbuf + P.in_buf];
-            for (int j = lane; j < ncopy; j += 32)
+            for (int j = lane; j < ncopy_e; j += 32)
                 dst[j] = (j >= jlo && j < jhi) ? load_elem(ib.ptr, ib.dtype, (int64_t)c * ib.ld + p0 + j) : 0.0;
         } else {
-            for (int j = lane; j < ncopy; j += 32) dst[j] = 0.0;
+            for (int j = lane; j < ncopy_e; j += 32) dst[j] = 0.0;
         }
     }
-    for (int i = tid; i < RB * 8; i += kFirThreads) xs[(size_t)(i >> 3) * P.xpitch + ncopy + (i & 7)] = 0.0;
+    for (int i = tid; i < RB * 8; i += kFirThreads) xs[(size_t)(i >> 3) * P.xpitch + ncopy_e + (i & 7)] = 0.0;
     asm volatile("cp.async.commit_group;" ::: "memory");
 
     // ---- 2. merged taps while the copies fly: 4 threads per output

@@ -486,7 +486,7 @@ FirGeom fir_geometry(const FirDerived& f, int tapsper, int G, int max_stack, int
     const int T = 8 * W, ypitch = T + 2, pmax = W == 8 ? f.pmax : f.pmax32;
     g.hbase = (f.dpad + 2) & ~1;                                   // even, >= dmax + 1
     g.tpad = (g.hbase + tapsper + f.dpad + 5 + 8) & ~1;            // + 8: slack read by the 4-pair unrolled tail
-    const int need = pmax + 3 + 8;                               // positions of a tile (+ even start, pair tail, unroll slack)
+    const int need = pmax + 4 + 8;                               // positions of a tile (+ even start, pair tail rounded to a pair, unroll slack)
     g.xpitch = need + ((2 - need % 4) + 4) % 4;                    // = 2 mod 4: lane=row 128-bit reads conflict free
     const size_t xrows = (size_t)std::max(g.xpitch, ypitch);
     g.smem = ((size_t)T * g.tpad + (size_t)32 * G * xrows + (size_t)max_stack * 2 * W * 32) * sizeof(double);
