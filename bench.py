@@ -426,7 +426,8 @@ def e2e_run(ctx, cp, x_dev, ninst, steps, barrier, pinned):
     xh = torch.empty((ninst, NCH, N_IN), dtype=torch.float64, pin_memory=pinned)
     yh = torch.empty((ninst, NCH, N_OUT), dtype=torch.float64, pin_memory=pinned)
     for i0 in range(0, ninst, 64):
-        xh[i0:i0 + 64].copy_(x_dev[i0:i0 + 64])
+        i1 = min(ninst, i0 + 64)
+        xh[i0:i1].copy_(x_dev[i0:i1])
     if not pinned:
         yh.zero_()                                   # touch the pages: first-touch faults are not the library's cost
     hin = cabi.CompiledPlan.host_buffers([xh[i].numpy().T for i in range(ninst)])
