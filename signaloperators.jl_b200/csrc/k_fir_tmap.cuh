@@ -17,7 +17,7 @@
 //     the signal, past its end, and rows past the last one are zero-filled by the TMA unit —
 //     the history before the first sample and the reference's zero padding (src/filters.jl:240);
 //   * finished 32-output tiles are staged in shared memory (two 16-output swizzled boxes) and
-//     written with two `cp.async.bulk.tensor.2d` stores by a store thread (whole 128-byte lines;
+//     written with `cp.async.bulk.tensor.2d` stores (16 outputs x 64 rows each) by one store thread per row half (whole 128-byte lines;
 //     columns past n_out and rows past the last are clipped by the tensor bounds);
 //   * the compute warps do nothing but LDS + DMMA + 16 shared-memory stores per tile.  Shared-memory
 //     bandwidth is the co-critical resource (ncu on the first version: LSU wavefronts + TMA traffic busy 70 %
@@ -41,6 +41,8 @@
 // k_fir_mma / k_fir.  SIGOPS_NO_FIR_TMAP=1 switches this kernel off.
 #pragma once
 #include <cuda.h>
+
+#include <type_traits>
 
 #include "k_fir_mma.cuh"
 
@@ -71,11 +73,9 @@ struct FirTmParams {
     const double* alpha;    // [m] fractional phase
     int tab_doubles;
     double gain;            // folded into the taps
-    int aligned;            // 1: band row 0 = the group's first window position rounded down to a multiple of 4 ring
-                            //    positions (compute warps share A blocks between groups, G > 1); 0: exactly that position
     long long* dbg;         // optional [blocks][8] cycle counters (tuning aid, SIGOPS_FIR_DBG=1), or nullptr
     int exp;                // tuning experiments (SIGOPS_FIR_EXP bit mask; wrong results): 1 no staging stores, 2 no tensor
-                            // stores, 4 no tap-band building
+                            // stores, 4 no tap-band building, 8 no ring loads, 16 compute warps do not wait for bands / data
 };
 
 inline size_t fir_tm_smem_bytes(int nslot, int ks, int tab_doubles, bool has_dpfb) {
@@ -105,12 +105,27 @@ __device__ __forceinline__ void sts_v2f64(unsigned a, double x, double y) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
 }
 
-template <bool SSQ, int G>
+__device__ __forceinline__ void mbar_wait_a(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <bool SSQ, bool DBG = false>
 __global__ void __launch_bounds__(kFtThreads, 1)
 k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtensorMap tm_in,
            const __grid_constant__ CUtensorMap tm_out) {
     extern __shared__ unsigned char ft_smem_raw[];
-    __shared__ uint64_t bar_full[kFtMaxSlots], bar_done[4], bar_taps[2], bar_stg_full, bar_stg_free;
+    __shared__ uint64_t bar_full[kFtMaxSlots], bar_done[4], bar_taps[2], bar_stg_full[2], bar_stg_free[2];
     // tiles finished, counted once per compute warp: what the producer polls.  (A plain counter, not the
     // `done` barriers: with strong up-sampling the ring holds many tiles, the producer may trail the compute
     // warps by more than the two phases a parity wait can tell apart.)
@@ -138,8 +153,10 @@ k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtens
         for (int i = 0; i < 4; ++i) mbar_init(&bar_done[i], kFtNCW);
         mbar_init(&bar_taps[0], kFtNAW * 32);
         mbar_init(&bar_taps[1], kFtNAW * 32);
-        mbar_init(&bar_stg_full, kFtNCW);
-        mbar_init(&bar_stg_free, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_stg_full[i], kFtNCW / 2);
+            mbar_init(&bar_stg_free[i], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_async_smem();
@@ -151,240 +168,228 @@ k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtens
     const unsigned band_tile = 4u * (unsigned)P.ks * 64u;      // bytes per band buffer
 
     if (warp < kFtNCW) {
-        // ---------------- DMMA: a warp owns F = 8/G row fragments (8F rows) x G consecutive output groups of the tile ----------------
-        // The k axis is walked in blocks of 4 positions aligned to the ring (position mod 4 == 0): the A
-        // fragments of a block are loaded once and feed every group of the warp whose band covers the block.
+        // ---------------- DMMA: a warp owns 8 row fragments (64 rows) x one 8-output group of the tile ----------------
         // Two compute warps per sub-partition: a single one cannot hide its own index arithmetic and operand
         // loads behind its DMMAs (measured with 4 warps x 16 fragments: 39 cycles per DMMA instead of 16).
-        constexpr int F = 8 / G;
-        const int gw = warp % (4 / G), rw = warp / (4 / G);
-        const int g0 = G * gw;                                           // my first output group
+        // A warp issues in order, so every integer instruction between two DMMAs is time the tensor pipe may
+        // idle (two warps at ~7 instructions per DMMA barely cover its 16 cycles): the k-loop below is written
+        // so that a block of 4 positions costs 9 LDS + 8 DMMA + a select and an add.
+        constexpr int F = 8;
+        const int gw = warp & 3, rw = warp >> 2;                         // output group, row half
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kFtRegsCompute));
         const int kk = lane & 3, rr = lane >> 2;
         const int rmap = ((rr & 1) << 2) | (rr & 2) | (rr >> 2);        // 3-bit reversal
         const int rloc = rw * (8 * F) + rmap;                            // fragment i holds row rloc + 8i
-        const unsigned key0 = (unsigned)rmap << 4;                       // swizzle: 16-byte chunk ^= row & 7
         const int nn = rr ^ ((kk >> 1) << 2);                            // band column after the XOR
         // (opaque to the optimiser: otherwise ptxas re-derives these from the thread index inside the k-loop —
         //  S2R + a dozen integer instructions per k-step — instead of keeping a few registers)
-        unsigned arow = ring + rloc * 128 + ((unsigned)(kk * 8) ^ key0);  // my element of block 0 of slot 0, swizzled
-        unsigned key = key0;
+        unsigned key = (unsigned)rmap << 4;                              // swizzle: 16-byte chunk ^= row & 7
         unsigned srow = stg + rloc * 128;
-        unsigned bcol = (unsigned)(kk * 64 + nn * 8);                    // my B element inside a 4-row band block
-        unsigned arow1 = ring + rloc * 128;                              // (G == 1) my row of slot 0
-        asm volatile("" : "+r"(arow), "+r"(key), "+r"(srow), "+r"(bcol), "+r"(arow1));
+        unsigned bcol = (unsigned)((gw * P.ks + kk) * 64 + nn * 8);      // my B element of block 0 inside a band buffer
+        unsigned arow1 = ring + rloc * 128;                              // my row of slot 0 (low 7 bits free for the offset)
+        unsigned ring_end = arow1 + (unsigned)P.nslot * kFtSlotBytes;
+        // barrier addresses and the lane-0 flag, kept in registers (re-derived per use they cost an S2R + LEA each)
+        unsigned a_taps = smem_u32(&bar_taps[0]), a_free = smem_u32(&bar_stg_free[rw]), a_full = smem_u32(&bar_stg_full[rw]);
+        unsigned a_done = smem_u32(&bar_done[0]), a_cnt = smem_u32(&done_count), lead = lane == 0 ? 1u : 0u;
+        asm volatile("" : "+r"(key), "+r"(srow), "+r"(bcol), "+r"(arow1), "+r"(ring_end));
+        asm volatile("" : "+r"(a_taps), "+r"(a_free), "+r"(a_full), "+r"(a_done), "+r"(a_cnt), "+r"(lead));
+        const int nt = (int)(t1 - t0);                                   // tiles of this block
+        const int64_t* xp = P.xi0 + t0 * kFmT + 8 * gw;                  // my group's entries of the index table
         double ssq[SSQ ? 8 : 1];
 #pragma unroll
         for (int i = 0; i < (SSQ ? 8 : 1); ++i) ssq[i] = 0.0;
 
-        // index tables, read one tile ahead: first / last output of every group, last output of the tile
-        int64_t xq_nx[G], x7_nx[G];
-        auto fetch_idx = [&](int64_t t) {
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                xq_nx[g] = __ldg(P.xi0 + t * kFmT + 8 * (g0 + g));
-                x7_nx[g] = __ldg(P.xi0 + t * kFmT + 8 * (g0 + g) + 7);
-            }
+        // index tables, read one tile ahead: first / last output of my group
+        int64_t xq_nx, x7_nx;
+        auto fetch_idx = [&](int u) {
+            xq_nx = __ldg(xp + (int64_t)u * kFmT);
+            x7_nx = __ldg(xp + (int64_t)u * kFmT + 7);
         };
-        fetch_idx(t0);
-        long long dbg_acc[3] = {0, 0, 0};
+        fetch_idx(0);
+        long long dbg_acc[5] = {0, 0, 0, 0, 0};   // (DBG) wait taps, set-up, wait staging, staging, -
 
-        // the tile in flight: first aligned block (global index and ring slot / quarter), blocks in all, and per
-        // group the first block and the number of blocks of its band
-        int64_t blk0 = 0;                               // global block index (position / 4 relative to pos_base) of the block loaded last
-        int slot = 0, sub = 0;                          // its ring slot and quarter of the slot (G == 1: per lane, byte offset in the row)
-        int64_t jcur = 0;                               // (G == 1) global slot index behind `slot`
-        int nbt = 0, ob[G], nb[G];
-        unsigned bandbase = 0;
-        struct Ops { double a[F], b[G]; };
+        // The band starts at the group's own first window position, so every lane tracks its own position
+        // p = first + kk + 4b.  Four blocks are 16 positions = one ring slot: within a tile, block b = 4c + J sits
+        // at byte ((sub0 + 32J) & 127) of the lane's row, in slot c or c + 1 of the tile (w[J]) — per tile four
+        // offsets (swizzle key folded in) and three flags, per block one select.
+        unsigned cur = arow1, nxt = arow1;              // my row in the slots c, c + 1 of the tile
+        int jcur = 0;                                   // global slot index behind `cur`
+        unsigned off[4];
+        bool w[4];
+        unsigned bq = 0;                                // my B element of the next block to load
+        int nbt = 0;                                    // blocks of the tile in flight
+        struct Ops { double a[F], b; };
         Ops o0, o1;
 
-        auto load_ops = [&](Ops& o, int b, unsigned bb, const int (&obx)[G], const int (&nbx)[G]) {
-            // G > 1: blocks are ring-aligned, (slot, sub) are warp-uniform; low 7 address bits = (kk*8 ^ swizzle key)
-            // from `arow`, quarter of the slot in bits 5-6.  G == 1: the band starts at the group's own first
-            // window position, every lane tracks its own position (slot, byte offset `sub` in the 128-byte row).
-            const unsigned ap = G > 1 ? (arow + (unsigned)slot * kFtSlotBytes) ^ (unsigned)(sub << 5)
-                                      : arow1 + (unsigned)slot * kFtSlotBytes + ((unsigned)sub ^ key);
+        auto load_ops = [&](Ops& o, auto J) {
+            const unsigned ap = (w[J.value] ? nxt : cur) + off[J.value];
 #pragma unroll
             for (int i = 0; i < F; ++i) o.a[i] = lds_f64(ap + i * 1024);
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                int kb = b - obx[g];                    // clamped: groups that do not cover the block load a row they own anyway
-                kb = kb < 0 ? 0 : (kb >= nbx[g] ? nbx[g] - 1 : kb);
-                o.b[g] = lds_f64(bb + (unsigned)((g0 + g) * P.ks + 4 * kb) * 64u + bcol);
-            }
+            o.b = lds_f64(bq);
+            bq += 256;
         };
-        auto advance = [&]() {                           // next block of 4 positions along the ring
-            ++blk0;
-            if (G > 1) {
-                if (++sub == 4) {
-                    sub = 0;
-                    if (++slot == P.nslot) slot = 0;
-                }
-            } else {
-                sub += 32;
-                if (sub >= 128) {
-                    sub -= 128;
-                    ++jcur;
-                    if (++slot == P.nslot) slot = 0;
-                }
-            }
+        auto next_slot = [&]() {                         // c -> c + 1
+            ++jcur;
+            cur = nxt;
+            nxt += kFtSlotBytes;
+            if (nxt == ring_end) nxt = arow1;
         };
-        // Set tile t up (index arithmetic, barrier waits) and load the operands of its first block into `o`.
+        // Set tile t up (index arithmetic, barrier wait) and load the operands of its first block into `o`.
         // Runs underneath the last block of the tile before it.
-        auto setup = [&](int64_t t, Ops& o) {
-            const int64_t u = t - t0;
-            const int s = (int)(u & 1);
-            int64_t ab[G];
-            int last = 0;
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const int64_t r = xq_nx[g] - P.tapsper + 1 - pos_base;               // >= 0: first window position of the group
-                ab[g] = r >> 2;
-                nb[g] = (int)(((G > 1 ? (r & 3) : 0) + (x7_nx[g] - xq_nx[g]) + P.tapsper + 3) >> 2);
-                nb[g] = nb[g] < (P.ks >> 2) ? nb[g] : (P.ks >> 2);
-            }
-            const int64_t rlane = xq_nx[0] - P.tapsper + 1 - pos_base + kk;          // (G == 1) my position of block 0
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                ob[g] = (int)(ab[g] - ab[0]);
-                last = last > ob[g] + nb[g] ? last : ob[g] + nb[g];
-            }
-            nbt = last;
-            if (t + 1 < t1) fetch_idx(t + 1);
-            // ring position of the tile's first block, relative to the block loaded last (the end of the tile in
-            // flight): a few blocks back, windows overlap
-            if (G > 1) {
-                const int adv = (int)(ab[0] - blk0);
-                blk0 = ab[0];
-                sub += adv;
-                slot += sub >> 2;                       // (arithmetic shift: floor for negative steps)
-                sub &= 3;
-            } else {
-                const int64_t j_new = rlane >> 4;       // global slot index of my position of block 0
-                slot += (int)(j_new - jcur);
-                jcur = j_new;
-                sub = (int)(rlane & 15) << 3;
-            }
+        auto setup = [&](int u, Ops& o) {
+            const long long cs = DBG ? clock64() : 0;
+            const int s = u & 1;
+            const int r = (int)(xq_nx - P.tapsper + 1 - pos_base) + kk;            // >= 0: my position of block 0
+            int n = (int)(x7_nx - xq_nx) + P.tapsper + 3;
+            n >>= 2;
+            nbt = n < (P.ks >> 2) ? n : (P.ks >> 2);
+            if (u + 1 < nt) fetch_idx(u + 1);
+            // ring slot of the tile's first block, relative to the slot in use (windows overlap: a step back is normal)
+            const int j_new = r >> 4;
+            int slot = (int)((cur - arow1) / kFtSlotBytes) + (j_new - jcur);
             while (slot >= P.nslot) slot -= P.nslot;
             while (slot < 0) slot += P.nslot;
-            bandbase = bands + s * band_tile;
+            jcur = j_new;
+            cur = arow1 + (unsigned)slot * kFtSlotBytes;
+            nxt = cur + kFtSlotBytes;
+            if (nxt == ring_end) nxt = arow1;
+            const unsigned sub0 = (unsigned)(r & 15) << 3;
+#pragma unroll
+            for (int J = 0; J < 4; ++J) {
+                const unsigned q = sub0 + 32u * J;
+                w[J] = q >= 128u;
+                off[J] = (q & 127u) ^ key;
+            }
+            bq = bands + s * band_tile + bcol;
             // one barrier per tile: the helpers arrive on it once the tile's band is built AND its ring slots
             // have landed (they watch the `full` barriers, off the compute warps' path)
-            const long long c0 = P.dbg ? clock64() : 0;
-            mbar_wait(&bar_taps[s], (unsigned)(u >> 1) & 1u);
-            if (P.dbg) dbg_acc[0] += clock64() - c0;
-            load_ops(o, 0, bandbase, ob, nb);
+            const long long c0 = DBG ? clock64() : 0;
+            if (!(P.exp & 16)) mbar_wait_a(a_taps + 8u * s, (unsigned)(u >> 1) & 1u);
+            if (DBG) dbg_acc[0] += clock64() - c0;
+            load_ops(o, std::integral_constant<int, 0>{});
+            if (DBG) dbg_acc[1] += clock64() - cs;
         };
-        auto mma_block = [&](double (&acc)[F][G][2], const Ops& o, int b, const int (&obx)[G], const int (&nbx)[G]) {
+        auto mma_block = [&](double (&acc)[F][2], const Ops& o) {
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-                if (G == 1 || (b >= obx[g] && b < obx[g] + nbx[g])) {
-#pragma unroll
-                    for (int i = 0; i < F; ++i) dmma884(acc[i][g][0], acc[i][g][1], o.a[i], o.b[g]);
-                }
-            }
+            for (int i = 0; i < F; ++i) dmma884(acc[i][0], acc[i][1], o.a[i], o.b);
         };
-        // fragments of a finished tile -> staging (the store thread has read the tile before it out of it)
-        auto stage_out = [&](double (&o)[F][G][2], int64_t u_old) {
-            const long long c0 = P.dbg ? clock64() : 0;
-            if (u_old > 0) mbar_wait(&bar_stg_free, (unsigned)(u_old - 1) & 1u);
-            if (P.dbg) dbg_acc[2] += clock64() - c0;
+        // fragments of a finished tile -> staging (the store thread has read the tile before it out of it).  The
+        // hand-over is split: the stores go out under the first block of the next tile, the proxy fence and the
+        // arrival two blocks later — issued right behind the stores the fence would hold the warp (and its DMMAs)
+        // until they have drained through the LSU queue (~400 cycles per tile, measured).
+        auto stage_store = [&](double (&o)[F][2], int u_old) {
+            const long long c0 = DBG ? clock64() : 0;
+            if (u_old > 0) mbar_wait_a(a_free, (unsigned)(u_old - 1) & 1u);
+            if (DBG) dbg_acc[2] += clock64() - c0;
             if (!(P.exp & 1)) {
+                const unsigned sp = srow + (gw >> 1) * 16384 + ((unsigned)(((gw & 1) * 4 + kk) << 4) ^ key);
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const int gg = g0 + g;
-                    const unsigned sp = srow + (gg >> 1) * 16384 + ((unsigned)(((gg & 1) * 4 + kk) << 4) ^ key);
-#pragma unroll
-                    for (int i = 0; i < F; ++i) sts_v2f64(sp + i * 1024, o[i][g][0], o[i][g][1]);
-                }
+                for (int i = 0; i < F; ++i) sts_v2f64(sp + i * 1024, o[i][0], o[i][1]);
             }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_stg_full);
             if (SSQ) {
                 // outputs past n_out have all-zero taps, rows past the last read zeros: exactly 0
 #pragma unroll
-                for (int i = 0; i < F; ++i)
-#pragma unroll
-                    for (int g = 0; g < G; ++g)
-                        ssq[G * i + g] = fma(o[i][g][0], o[i][g][0], fma(o[i][g][1], o[i][g][1], ssq[G * i + g]));
+                for (int i = 0; i < F; ++i) ssq[i] = fma(o[i][0], o[i][0], fma(o[i][1], o[i][1], ssq[i]));
             }
+            if (DBG) dbg_acc[3] += clock64() - c0;
+        };
+        auto stage_signal = [&]() {
+            const long long c0 = DBG ? clock64() : 0;
+            fence_async_smem();
+            __syncwarp();
+            if (lead) mbar_arrive_a(a_full);
+            if (DBG) dbg_acc[3] += clock64() - c0;
         };
         // One tile: its DMMAs accumulate into `acc` while the fragments of the tile before it (`old`) drain to
-        // the staging boxes underneath them and, during the last block, the next tile is set up and its
+        // the staging boxes underneath its first block and, during the last block, the next tile is set up and its
         // first operands are fetched: the tensor pipe is never left waiting for a tile boundary.  On entry
-        // o0 holds the operands of block 0; on exit it holds those of the next tile's.
-        auto tile = [&](double (&acc)[F][G][2], double (&old)[F][G][2], int64_t t) {
-            const int64_t u = t - t0;
-            const bool more = t + 1 < t1;
+        // o0 holds the operands of block 0; on exit it holds those of the next tile's.  Blocks alternate between
+        // o0 (even) and o1 (odd); J = b mod 4 is a compile-time constant in every step.
+        auto tile = [&](double (&acc)[F][2], double (&old)[F][2], int u) {
+            const bool more = u + 1 < nt;
 #pragma unroll
-            for (int i = 0; i < F; ++i)
-#pragma unroll
-                for (int g = 0; g < G; ++g) acc[i][g][0] = acc[i][g][1] = 0.0;
-            // this tile's schedule (setup of the next tile overwrites the shared copies)
+            for (int i = 0; i < F; ++i) acc[i][0] = acc[i][1] = 0.0;
             const int n = nbt;
-            const unsigned bb = bandbase;
-            int obt[G], nbx[G];
-#pragma unroll
-            for (int g = 0; g < G; ++g) { obt[g] = ob[g]; nbx[g] = nb[g]; }
-            if (n >= 2) {
-                advance();
-                load_ops(o1, 1, bb, obt, nbx);
-                mma_block(acc, o0, 0, obt, nbx);
-                if (u > 0) stage_out(old, u - 1);
-                int b = 1;                                    // o1 holds block b
-                for (; b + 2 < n; b += 2) {
-                    advance();
-                    load_ops(o0, b + 1, bb, obt, nbx);
-                    mma_block(acc, o1, b, obt, nbx);
-                    advance();
-                    load_ops(o1, b + 2, bb, obt, nbx);
-                    mma_block(acc, o0, b + 1, obt, nbx);
-                }
-                if (n - b == 2) {
-                    advance();
-                    load_ops(o0, b + 1, bb, obt, nbx);
-                    mma_block(acc, o1, b, obt, nbx);
-                    if (more) setup(t + 1, o1);
-                    mma_block(acc, o0, b + 1, obt, nbx);
-                    o0 = o1;
+            using I0 = std::integral_constant<int, 0>;
+            using I1 = std::integral_constant<int, 1>;
+            using I2 = std::integral_constant<int, 2>;
+            using I3 = std::integral_constant<int, 3>;
+            int b = 0;
+            bool signalled = u == 0;
+            while (true) {
+                // J = 0 (o0)
+                if (b + 1 < n) {
+                    load_ops(o1, I1{});
+                    mma_block(acc, o0);
+                    if (b == 0 && u > 0) stage_store(old, u - 1);
                 } else {
-                    if (more) setup(t + 1, o0);
-                    mma_block(acc, o1, b, obt, nbx);
+                    if (more) setup(u + 1, o1);
+                    mma_block(acc, o0);
+                    if (b == 0 && u > 0) stage_store(old, u - 1);
+                    o0 = o1;
+                    break;
                 }
-            } else {
-                if (more) setup(t + 1, o1);
-                mma_block(acc, o0, 0, obt, nbx);
-                if (u > 0) stage_out(old, u - 1);
-                o0 = o1;
+                ++b;
+                // J = 1 (o1)
+                if (b + 1 < n) {
+                    load_ops(o0, I2{});
+                    mma_block(acc, o1);
+                } else {
+                    if (more) setup(u + 1, o0);
+                    mma_block(acc, o1);
+                    break;
+                }
+                ++b;
+                // J = 2 (o0)
+                if (b + 1 < n) {
+                    load_ops(o1, I3{});
+                    mma_block(acc, o0);
+                    if (b == 2 && u > 0) { stage_signal(); signalled = true; }
+                } else {
+                    if (more) setup(u + 1, o1);
+                    mma_block(acc, o0);
+                    o0 = o1;
+                    break;
+                }
+                ++b;
+                // J = 3 (o1)
+                if (b + 1 < n) {
+                    next_slot();
+                    load_ops(o0, I0{});
+                    mma_block(acc, o1);
+                } else {
+                    if (more) setup(u + 1, o0);
+                    mma_block(acc, o1);
+                    break;
+                }
+                ++b;
             }
+            if (!signalled) stage_signal();               // (tiles of fewer than four blocks)
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&bar_done[u & 3]);
-                asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(&done_count)) : "memory");
+            if (lead) {
+                mbar_arrive_a(a_done + 8u * (u & 3));
+                asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(a_cnt) : "memory");
             }
         };
 
-        double accA[F][G][2], accB[F][G][2];
-        setup(t0, o0);
-        const long long cstart = P.dbg ? clock64() : 0;
-        for (int64_t t = t0; t < t1; t += 2) {
-            tile(accA, accB, t);
-            if (t + 1 < t1) tile(accB, accA, t + 1);
+        double accA[F][2], accB[F][2];
+        setup(0, o0);
+        const long long cstart = DBG ? clock64() : 0;
+        for (int u = 0; u < nt; u += 2) {
+            tile(accA, accB, u);
+            if (u + 1 < nt) tile(accB, accA, u + 1);
         }
-        if (P.dbg && warp == 0 && lane == 0) {
+        if (DBG && warp == 0 && lane == 0) {
             long long* d = P.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8;
-            d[0] = dbg_acc[0]; d[1] = 0; d[2] = dbg_acc[2]; d[3] = clock64() - cstart;
+            d[0] = dbg_acc[0]; d[1] = dbg_acc[1]; d[2] = dbg_acc[2]; d[3] = clock64() - cstart; d[6] = dbg_acc[3];
         }
-        if ((t1 - t0) & 1) stage_out(accA, t1 - t0 - 1);
-        else stage_out(accB, t1 - t0 - 1);
+        if (nt & 1) stage_store(accA, nt - 1);
+        else stage_store(accB, nt - 1);
+        stage_signal();
         if (SSQ) {
 #pragma unroll
             for (int i = 0; i < F; ++i) {
-                double v = 0.0;
-#pragma unroll
-                for (int g = 0; g < G; ++g) v += ssq[G * i + g];
+                double v = ssq[i];
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
                 const int64_t row = (int64_t)row0 + rloc + 8 * i;
@@ -433,47 +438,62 @@ k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtens
                 xe_nx = __ldg(P.xi0 + (t + 1) * kFmT + kFmT - 1);
             }
             const int64_t xg = __shfl_sync(0xffffffffu, xi, 0);
-            const int og = P.aligned ? (int)((xg - P.tapsper + 1 - pos_base) & 3) : 0;   // the group's window start inside its first aligned block
             // band rows [st, st + tapsper) hold column (lane & 7)'s taps; a dead column (past n_out) holds none
-            const int st = live ? (int)(xi - xg) + og : (1 << 20);
+            const int st = live ? (int)(xi - xg) : (1 << 20);
             // what my fragment elements need: C columns 2kk, 2kk+1; A columns kk, 4+kk; B column rr
             const int st_c0 = __shfl_sync(0xffffffffu, st, 2 * kk), st_c1 = __shfl_sync(0xffffffffu, st, 2 * kk + 1);
             const int po_c0 = __shfl_sync(0xffffffffu, po, 2 * kk), po_c1 = __shfl_sync(0xffffffffu, po, 2 * kk + 1);
             const int st_a0 = __shfl_sync(0xffffffffu, st, kk), st_a1 = __shfl_sync(0xffffffffu, st, 4 + kk);
             const int po_a0 = __shfl_sync(0xffffffffu, po, kk), po_a1 = __shfl_sync(0xffffffffu, po, 4 + kk);
             const double al_b = __shfl_sync(0xffffffffu, al, rr);
-            const double b0 = (kk == rr) ? al_b : 0.0, b1 = (4 + kk == rr) ? al_b : 0.0;
+            const double b0v = (kk == rr) ? al_b : 0.0, b1v = (4 + kk == rr) ? al_b : 0.0;
             const unsigned band = bands + s * band_tile + (unsigned)(grp * P.ks) * 64u;
             // tile t-2 must be finished: its band buffer is about to be overwritten
-            const long long c0 = P.dbg ? clock64() : 0;
+            const long long c0 = DBG ? clock64() : 0;
             if (u >= 2) mbar_wait(&bar_done[(u - 2) & 3], (unsigned)((u - 2) >> 2) & 1u);
-            const long long c1 = P.dbg ? clock64() : 0;
-            hdbg[0] += c1 - c0;
-            for (int b = 0; b < ((P.exp & 4) ? 0 : nblk); ++b) {
-                const int k = 8 * b + rr;                                        // my band row
-                const unsigned tc0 = (unsigned)(k - st_c0), tc1 = (unsigned)(k - st_c1);   // tap indices (unsigned: one range test)
-                const unsigned ta0 = (unsigned)(k - st_a0), ta1 = (unsigned)(k - st_a1);
-                double cv0 = tc0 < (unsigned)P.tapsper ? lds_f64(pf_tab + 8u * ((unsigned)po_c0 + tc0)) : 0.0;
-                double cv1 = tc1 < (unsigned)P.tapsper ? lds_f64(pf_tab + 8u * ((unsigned)po_c1 + tc1)) : 0.0;
-                if (has_d) {
-                    const double a0 = ta0 < (unsigned)P.tapsper ? lds_f64(dpf_tab + 8u * ((unsigned)po_a0 + ta0)) : 0.0;
-                    const double a1 = ta1 < (unsigned)P.tapsper ? lds_f64(dpf_tab + 8u * ((unsigned)po_a1 + ta1)) : 0.0;
-                    dmma884(cv0, cv1, a0, b0);
-                    dmma884(cv0, cv1, a1, b1);
+            const long long c1 = DBG ? clock64() : 0;
+            if (DBG) hdbg[0] += c1 - c0;
+            // batches of four 8-row blocks: all table look-ups first, then the (independent) DMMAs, then the stores —
+            // a helper's instructions queue behind the compute warps' DMMA stream, so a dependent
+            // look-up -> DMMA -> DMMA -> store chain per block would pay that queueing four times per block
+            for (int b0 = 0; b0 < ((P.exp & 4) ? 0 : nblk); b0 += 4) {
+                double cv0[4], cv1[4], a0[4], a1[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = 8 * (b0 + i) + rr;                                 // my band row
+                    const bool on = b0 + i < nblk;
+                    const unsigned tc0 = (unsigned)(k - st_c0), tc1 = (unsigned)(k - st_c1);   // tap indices (unsigned: one range test)
+                    const unsigned ta0 = (unsigned)(k - st_a0), ta1 = (unsigned)(k - st_a1);
+                    cv0[i] = on && tc0 < (unsigned)P.tapsper ? lds_f64(pf_tab + 8u * ((unsigned)po_c0 + tc0)) : 0.0;
+                    cv1[i] = on && tc1 < (unsigned)P.tapsper ? lds_f64(pf_tab + 8u * ((unsigned)po_c1 + tc1)) : 0.0;
+                    a0[i] = has_d && on && ta0 < (unsigned)P.tapsper ? lds_f64(dpf_tab + 8u * ((unsigned)po_a0 + ta0)) : 0.0;
+                    a1[i] = has_d && on && ta1 < (unsigned)P.tapsper ? lds_f64(dpf_tab + 8u * ((unsigned)po_a1 + ta1)) : 0.0;
                 }
-                // columns 2kk, 2kk+1 stay adjacent under the XOR on bit 2 of the column index
-                sts_v2f64(band + 8u * (unsigned)(k * 8 + ((2 * kk) ^ (((k >> 1) & 1) << 2))), cv0, cv1);
+                if (has_d) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (b0 + i < nblk) dmma884(cv0[i], cv1[i], a0[i], b0v);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (b0 + i < nblk) dmma884(cv0[i], cv1[i], a1[i], b1v);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = 8 * (b0 + i) + rr;
+                    // columns 2kk, 2kk+1 stay adjacent under the XOR on bit 2 of the column index
+                    if (b0 + i < nblk) sts_v2f64(band + 8u * (unsigned)(k * 8 + ((2 * kk) ^ (((k >> 1) & 1) << 2))), cv0[i], cv1[i]);
+                }
             }
             // ... and the tile's window has landed in the ring
-            while (jwait < hi) {
+            while (jwait < hi && !(P.exp & 8)) {
                 mbar_wait(&bar_full[jw_slot], jw_par);
                 ++jwait;
                 if (++jw_slot == P.nslot) { jw_slot = 0; jw_par ^= 1u; }
             }
             mbar_arrive(&bar_taps[s]);
-            if (P.dbg) hdbg[1] += clock64() - c1;
+            if (DBG) hdbg[1] += clock64() - c1;
         }
-        if (P.dbg && grp == 0 && lane == 0) {
+        if (DBG && grp == 0 && lane == 0) {
             long long* d = P.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8;
             d[4] = hdbg[0]; d[5] = hdbg[1];
         }
@@ -482,7 +502,7 @@ k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtens
       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kFtRegsMisc));
       if (warp == kFtNCW + kFtNAW) {
         // ---------------- producer: one tensor copy per ring slot, as far ahead as the ring allows ----------------
-        if (lane == 0) {
+        if (lane == 0 && !(P.exp & 8)) {
             const int64_t last_need = __ldg(P.xi0 + (t1 - 1) * kFmT + kFmT - 1) + 1;
             const int64_t nslots_total = (last_need - pos_base + (kFtSlotPos - 1)) >> 4;
             auto lo_of = [&](int64_t t) { return (__ldg(P.xi0 + t * kFmT) - P.tapsper + 1 - pos_base) >> 4; };
@@ -499,29 +519,34 @@ k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtens
                     }
                     const unsigned target = (unsigned)(tp - t0 + 1) * kFtNCW;
                     unsigned seen;
-                    do {
+                    // (polled with a pause: a spinning warp takes issue slots from the compute warps of its sub-partition)
+                    while (true) {
                         asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(&done_count)) : "memory");
-                    } while (seen < target);
+                        if (seen >= target) break;
+                        if (P.exp & 32) __nanosleep(64);
+                    }
                 }
                 mbar_expect_tx(&bar_full[s], kFtSlotBytes);
                 tmap_load_2d(ring + (unsigned)s * kFtSlotBytes, &tm_in, (int)(pos_base + j * kFtSlotPos), row0, &bar_full[s]);
                 if (++s == P.nslot) s = 0;
             }
         }
-      } else if (warp == kFtNCW + kFtNAW + 1) {
-        // ---------------- store: two tensor stores per tile out of the staging boxes ----------------
-        if (lane == 0) {
+      } else {
+        // ---------------- store: one thread per row half, two tensor stores (16 outputs x 64 rows) per tile ----------------
+        const int h = warp - (kFtNCW + kFtNAW + 1);
+        if (h < 2 && lane == 0) {
+            const bool rows_live = (int64_t)row0 + 64 * h < P.nrows;
             for (int64_t t = t0; t < t1; ++t) {
                 const int64_t u = t - t0;
-                mbar_wait(&bar_stg_full, (unsigned)u & 1u);
+                mbar_wait(&bar_stg_full[h], (unsigned)u & 1u);
                 const int64_t m0 = t * kFmT;
-                if (!(P.exp & 2)) {
-                    tmap_store_2d(&tm_out, (int)m0, row0, stg);
-                    if (m0 + 16 < P.n_out) tmap_store_2d(&tm_out, (int)(m0 + 16), row0, stg + 16384);
+                if (!(P.exp & 2) && rows_live) {
+                    tmap_store_2d(&tm_out, (int)m0, row0 + 64 * h, stg + 8192u * h);
+                    if (m0 + 16 < P.n_out) tmap_store_2d(&tm_out, (int)(m0 + 16), row0 + 64 * h, stg + 16384 + 8192u * h);
                 }
                 bulk_commit();
                 bulk_wait_read_all();
-                mbar_arrive(&bar_stg_free);
+                mbar_arrive(&bar_stg_free[h]);
             }
             bulk_wait_all();
         }

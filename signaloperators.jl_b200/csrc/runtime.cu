@@ -1202,8 +1202,8 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                 };
                 char *bin = nullptr, *bout = nullptr;
                 int64_t sin_ = 0, sout = 0;
-                // a group's band starts at its first window position rounded down to a multiple of 4 ring positions
-                const int ks = (int)round_up(s.fir.dpad + g.taps_per_phase + 3, 8);
+                // a group's band starts at its first window position; the helpers build it in blocks of 8 rows
+                const int ks = (int)round_up(s.fir.dpad + g.taps_per_phase, 8);
                 const int win_slots = (s.fir.pmax32 + 14) / 16 + 1;          // worst alignment of a tile's window
                 int nslot = kFtMaxSlots;
                 const bool has_d = P.dpfb != nullptr;
@@ -1213,7 +1213,7 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                 if (ks <= kFtMaxKs && nslot >= win_slots + 1 && fir_tm_smem_bytes(nslot, ks, (int)tabd_, has_d) <= kFirTmSmemLimit &&
                     uniform(s.fir.in_buf, bin, sin_) && uniform(g.out_buf, bout, sout) && s.fir.in_len >= 1 &&
                     tmap_encode_2d_f64(&mi, bin, s.fir.in_len, rows, sin_, kFtSlotPos, kFtRows) &&
-                    tmap_encode_2d_f64(&mo, bout, g.n_out, rows, sout, 16, kFtRows)) {
+                    tmap_encode_2d_f64(&mo, bout, g.n_out, rows, sout, 16, kFtRows / 2)) {
                     FirTmParams T{};
                     T.scalars = scalars; T.nscalars = nscal; T.sumsq_slot = g.sumsq_slot; T.nch = g.nchannels;
                     T.nrows = rows; T.n_out = g.n_out; T.tapsper = g.taps_per_phase; T.ks = ks; T.nslot = nslot;
@@ -1222,11 +1222,6 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                     T.tab_doubles = (int)tabd_;
                     T.gain = s.fir.epi_scale;
                     if (const char* e = getenv("SIGOPS_FIR_EXP")) T.exp = atoi(e);
-                    // output groups per compute warp: measured on config 3, sharing A blocks between groups (2: 1.79 ms,
-                    // 4: 2.20 ms) loses to one group per warp (1.43 ms) — the loop is bound by issue order, not by
-                    // shared-memory bandwidth — so 1 is the default and the others stay as tuning knobs
-                    const int gsel = getenv("SIGOPS_FIR_GROUPS") ? atoi(getenv("SIGOPS_FIR_GROUPS")) : 1;
-                    T.aligned = gsel == 1 ? 0 : 1;
                     const int64_t groups = (rows + kFtRows - 1) / kFtRows;
                     // segments along the time axis: whole waves of one block per SM; a segment pays about
                     // three tiles of start-up (first window, pipeline fill)
@@ -1259,8 +1254,8 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                             CUDA_OK(cudaMemset(dbg, 0, nb * 8 * sizeof(long long)));
                             FirTmParams D = T;
                             D.dbg = dbg;
-                            ensure_dyn_smem(k_fir_tmap<false, 1>, smem);
-                            k_fir_tmap<false, 1><<<tgrid, kFtThreads, smem, stream>>>(D, *(const CUtensorMap*)&mi, *(const CUtensorMap*)&mo);
+                            ensure_dyn_smem(k_fir_tmap<false, true>, smem);
+                            k_fir_tmap<false, true><<<tgrid, kFtThreads, smem, stream>>>(D, *(const CUtensorMap*)&mi, *(const CUtensorMap*)&mo);
                             CUDA_OK(cudaStreamSynchronize(stream));
                             std::vector<long long> h(nb * 8);
                             CUDA_OK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -1269,21 +1264,19 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                             for (size_t b = 0; b < nb; ++b)
                                 for (int k = 0; k < 8; ++k) sum[k] += (double)h[b * 8 + k];
                             const double per = 1.0 / ((double)nb * (double)best_tps);
-                            fprintf(stderr, "[sigops] FIR tmap cycles/tile  compute: wait_taps %.0f wait_full %.0f wait_stg %.0f total %.0f | helper: wait_done %.0f build %.0f\n",
-                                    sum[0] * per, sum[1] * per, sum[2] * per, sum[3] * per, sum[4] * per, sum[5] * per);
+                            fprintf(stderr, "[sigops] FIR tmap cycles/tile  compute: set-up %.0f (of it wait_taps %.0f) staging %.0f (of it wait_stg %.0f) total %.0f | helper: wait_done %.0f build %.0f\n",
+                                    sum[1] * per, sum[0] * per, sum[6] * per, sum[2] * per, sum[3] * per, sum[4] * per, sum[5] * per);
                         }
                         add(KIND_FIR, [=](cudaStream_t st) {
                             const CUtensorMap& a = *(const CUtensorMap*)&mi;
                             const CUtensorMap& b = *(const CUtensorMap*)&mo;
-#define SIGOPS_FIR_TM_CASE(SSQ_, G_)                                        \
-    {                                                                        \
-        ensure_dyn_smem(k_fir_tmap<SSQ_, G_>, smem);                         \
-        k_fir_tmap<SSQ_, G_><<<tgrid, kFtThreads, smem, st>>>(T, a, b);      \
+#define SIGOPS_FIR_TM_CASE(SSQ_)                                        \
+    {                                                                    \
+        ensure_dyn_smem(k_fir_tmap<SSQ_>, smem);                         \
+        k_fir_tmap<SSQ_><<<tgrid, kFtThreads, smem, st>>>(T, a, b);      \
     }
-                            if (ssq) SIGOPS_FIR_TM_CASE(true, 1)
-                            else if (gsel == 2) SIGOPS_FIR_TM_CASE(false, 2)
-                            else if (gsel == 4) SIGOPS_FIR_TM_CASE(false, 4)
-                            else SIGOPS_FIR_TM_CASE(false, 1)
+                            if (ssq) SIGOPS_FIR_TM_CASE(true)
+                            else SIGOPS_FIR_TM_CASE(false)
 #undef SIGOPS_FIR_TM_CASE
                         });
                         continue;
