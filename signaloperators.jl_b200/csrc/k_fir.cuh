@@ -145,19 +145,22 @@ k_fir(const __grid_constant__ FirParams P) {
         if (kind == 1) {
             const double* src = s_src[r];
             if ((((uintptr_t)src) & 15) == 0) {
-                // two positions per lane; a pair straddling the end of the signal reads 8 bytes
+                // two positions per lane; positions outside the signal (history before it, zero padding after it)
+                // are plain zero stores — not zero-size cp.async copies, which the sanitizer tools do not model
                 for (int j = 2 * lane; j < ncopy; j += 64) {
-                    const int nb = (j >= jlo && j < jhi) ? ((j + 1 < jhi) ? 16 : 8) : 0;
-                    if (j + 1 >= jlo && j < jlo) {            // pair straddling the start: element-wise
-                        cp_async8(dst + j, src + jlo, false);
-                        cp_async8(dst + j + 1, src + j + 1, j + 1 < jhi);
-                    } else
-                        cp_async16(dst + j, src + (nb ? j : jlo), nb);
+                    const bool in0 = j >= jlo && j < jhi, in1 = j + 1 >= jlo && j + 1 < jhi;
+                    if (in0 && in1) cp_async16(dst + j, src + j, 16);
+                    else {
+                        if (in0) cp_async8(dst + j, src + j, true);
+                        else dst[j] = 0.0;
+                        if (in1) cp_async8(dst + j + 1, src + j + 1, true);
+                        else dst[j + 1] = 0.0;
+                    }
                 }
             } else {
                 for (int j = lane; j < ncopy_e; j += 32) {
-                    const bool ok = j >= jlo && j < jhi;
-                    cp_async8(dst + j, src + (ok ? j : jlo), ok);
+                    if (j >= jlo && j < jhi) cp_async8(dst + j, src + j, true);
+                    else dst[j] = 0.0;
                 }
             }
         } else if (kind == 2) {
