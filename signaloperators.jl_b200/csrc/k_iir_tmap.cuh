@@ -119,7 +119,8 @@ __device__ __forceinline__ void apply_leaf16(int op, double* acc, const double* 
 
 template <int M, bool UNITB, class T, bool LV = false>
 __device__ __forceinline__ double cascade16_swz(Cascade<M>& f, unsigned char* row, int key, int blk, double gain, double sc, double sc2,
-                                                int nvalid, const IirTmapParams* P = nullptr, const double* lv = nullptr, int lvpitch = 0) {
+                                                int nvalid, bool want_ss, const IirTmapParams* P = nullptr, const double* lv = nullptr,
+                                                int lvpitch = 0, unsigned skip = 0u) {
     double xr[16];
     if (sizeof(T) == 8) {
 #pragma unroll
@@ -134,8 +135,11 @@ __device__ __forceinline__ double cascade16_swz(Cascade<M>& f, unsigned char* ro
             xr[4 * j] = v.x; xr[4 * j + 1] = v.y; xr[4 * j + 2] = v.z; xr[4 * j + 3] = v.w;
         }
     }
+    // (bit j of `skip`: operation j multiplies / divides by a leaf that is exactly 1 over this whole stage — a ramp
+    //  outside its short region — which is the identity, bit for bit)
     if (LV) {
-        for (int j = 0; j < P->n_in_ops; ++j) apply_leaf16(P->ops[j].op, xr, lv + j * lvpitch);
+        for (int j = 0; j < P->n_in_ops; ++j)
+            if (!((skip >> j) & 1u)) apply_leaf16(P->ops[j].op, xr, lv + j * lvpitch);
     }
     double pipe[M], out[16];
 #pragma unroll
@@ -146,13 +150,23 @@ __device__ __forceinline__ double cascade16_swz(Cascade<M>& f, unsigned char* ro
             if (k >= 0 && k < 16) {
                 const double in = (j == 0) ? xr[k] : pipe[j - 1];
                 pipe[j] = biquad_step<M, UNITB>(f, j, in);
-                if (j == M - 1) out[k] = ((pipe[j] * gain) * sc) * sc2;
+                if (j == M - 1) out[k] = pipe[j] * gain;
             }
         }
     }
+    // y = ((cascade * gain) * sc) * sc2, the epilogue's constants in order; a factor of exactly 1 is skipped (identity)
+    if (sc != 1.0) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) out[k] *= sc;
+    }
+    if (sc2 != 1.0) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) out[k] *= sc2;
+    }
     if (LV) {
         for (int j = 0; j < P->n_ep_ops; ++j)
-            apply_leaf16(P->ops[kTmMaxLeafOps + j].op, out, lv + (kTmMaxLeafOps + j) * lvpitch);
+            if (!((skip >> (kTmMaxLeafOps + j)) & 1u))
+                apply_leaf16(P->ops[kTmMaxLeafOps + j].op, out, lv + (kTmMaxLeafOps + j) * lvpitch);
     }
     if (sizeof(T) == 8) {
 #pragma unroll
@@ -166,9 +180,11 @@ __device__ __forceinline__ double cascade16_swz(Cascade<M>& f, unsigned char* ro
         }
     }
     double ss = 0.0;
+    if (want_ss) {                                   // only when a Normpower follows (warp-uniform)
 #pragma unroll
-    for (int k = 0; k < 16; ++k)
-        if (nvalid >= 16 || k < nvalid) ss = fma(out[k], out[k], ss);
+        for (int k = 0; k < 16; ++k)
+            if (nvalid >= 16 || k < nvalid) ss = fma(out[k], out[k], ss);
+    }
     return ss;
 }
 
@@ -190,7 +206,9 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
     __shared__ uint64_t bars[NW][NS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // 1024-byte aligned stage buffers (the swizzle pattern is a function of address bits 4-9)
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tm_smem_raw) + 1023) & ~uintptr_t(1023));
+    // (an offset into the shared array, not a pointer rebuilt from an integer: the latter turns every access of
+    //  the kernel into a generic LD/ST)
+    unsigned char* base = tm_smem_raw + ((1024u - (smem_u32(tm_smem_raw) & 1023u)) & 1023u);
     unsigned char* const stage0 = base + (size_t)warp * NS * kStageB;
     auto stage_of = [&](int b) { return stage0 + b * kStageB; };
     // (LV) the warp's leaf vectors: [2 * kTmMaxLeafOps][SC] doubles, the same for all 32 rows of the warp
@@ -238,6 +256,7 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
     };
 
     double ss = 0.0;
+    const bool want_ss = P.sumsq_slot >= 0;
     unsigned parity = 0u;
     for (int64_t h = 0; h < NS - 1 && h < nstage; ++h) issue_load(h);
     for (int64_t h = 0; h < nstage; ++h) {
@@ -250,6 +269,7 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
         unsigned char* rowp = stage_of(b) + lane * (SUBS * 128);
         const bool keep = off >= pre;                                  // pre is a multiple of the stage
         double s3 = 0.0;
+        unsigned skip = 0u;
         if (LV) {
             // the leaves of the fused programs depend on the frame only: every lane evaluates a few frames of the
             // stage (the interpreter's exact formulas), all 32 rows then read them back as broadcasts
@@ -264,6 +284,10 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
                 bool ones = false;                                     // ramps are 1 outside a short region
                 if (I->leaf == SIGOPS_LEAF_RAMP_ON) ones = n0 + I->i0 > I->i1;
                 else if (I->leaf == SIGOPS_LEAF_RAMP_OFF) ones = n0 + (SC - 1) + I->i0 <= I->i1;
+                if (ones && (I->op == SIGOPS_OP_MUL || I->op == SIGOPS_OP_DIV)) {
+                    skip |= 1u << j;
+                    continue;
+                }
                 for (int fr = lane; fr < SC; fr += 32) lvbuf[j * SC + fr] = ones ? 1.0 : rowinv_leaf(I, n0 + fr);
             }
             __syncwarp();
@@ -274,7 +298,7 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
             for (int blk = 0; blk < SUB / 16; ++blk) {
                 const int64_t rem = work - off - s * SUB - blk * 16;   // outputs of this block that exist
                 s3 += cascade16_swz<M, UNITB, T, LV>(f, rowp + s * 128, (SUBS * lane + s) & 7, blk, P.gain, P.scale, P.scale2,
-                                                     rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0), &P, lvbuf + s * SUB + blk * 16, SC);
+                                                     rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0), want_ss, &P, lvbuf + s * SUB + blk * 16, SC, skip);
             }
             if (s == 0 && h + NS - 1 < nstage) {
                 // the stage filtered one iteration ago went to a tensor store: once the TMA unit has
