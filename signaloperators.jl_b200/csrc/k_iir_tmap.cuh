@@ -211,12 +211,25 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
     unsigned char* base = tm_smem_raw + ((1024u - (smem_u32(tm_smem_raw) & 1023u)) & 1023u);
     unsigned char* const stage0 = base + (size_t)warp * NS * kStageB;
     auto stage_of = [&](int b) { return stage0 + b * kStageB; };
-    // (LV) the warp's leaf vectors: [2 * kTmMaxLeafOps][SC] doubles, the same for all 32 rows of the warp
-    double* const lvbuf = reinterpret_cast<double*>(base + (size_t)NW * NS * kStageB) + (size_t)warp * 2 * kTmMaxLeafOps * SC;
+    // (LV) the block's leaf vectors, double-buffered over stages: [2][2 * kTmMaxLeafOps][SC] doubles.  They depend on
+    // the frame only, so the warps of a block are given the SAME chunk of NW consecutive row groups and evaluate
+    // each value once per block (one leaf evaluation per thread and stage instead of four, all on the critical
+    // path of a kernel that is bound by its FP64 dependency chains: 30 % of the stall samples before).
+    double* const lvbuf = reinterpret_cast<double*>(base + (size_t)NW * NS * kStageB);
 
-    const int64_t unit = (int64_t)blockIdx.x * NW + warp;             // (row group, chunk)
-    if (unit >= P.nunits) return;
-    const int64_t grp = unit / P.cpr, k = unit % P.cpr;
+    int64_t grp, k;
+    bool active = true;
+    if (LV) {
+        const int64_t ngroups = P.nunits / P.cpr;
+        k = (int64_t)blockIdx.x % P.cpr;
+        grp = ((int64_t)blockIdx.x / P.cpr) * NW + warp;
+        active = grp < ngroups;                                        // (idle warps still take part in the leaf vectors)
+    } else {
+        const int64_t unit = (int64_t)blockIdx.x * NW + warp;         // (row group, chunk)
+        if (unit >= P.nunits) return;
+        grp = unit / P.cpr;
+        k = unit % P.cpr;
+    }
     const int64_t row = grp * 32 + lane;
     const bool live = row < P.nrows;
     const int64_t pre = k >= 1 ? P.Wc : 0;
@@ -248,7 +261,7 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
     // One tensor instruction per stage: box = (128 bytes, 5 blocks, 32 rows) of the
     // [row][frame/SUB][SUB] view, i.e. 640 contiguous bytes per row.
     auto issue_load = [&](int64_t h) {
-        if (lane == 0) {
+        if (lane == 0 && active) {
             const int b = (int)(h % NS);
             mbar_expect_tx(&bars[warp][b], kStageB);
             tmap_load_3d(stage_of(b), &tm_in, 0, (int)((start + h * SC) / SUB), c1, &bars[warp][b]);
@@ -261,7 +274,7 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
     for (int64_t h = 0; h < NS - 1 && h < nstage; ++h) issue_load(h);
     for (int64_t h = 0; h < nstage; ++h) {
         const int b = (int)(h % NS);
-        mbar_wait(&bars[warp][b], (parity >> b) & 1u);
+        if (active) mbar_wait(&bars[warp][b], (parity >> b) & 1u);
         parity ^= 1u << b;
         const int64_t off = h * SC;
         // smem box layout: [row][block][128 bytes]; the 128-byte swizzle XORs the 16-byte chunk index
@@ -270,35 +283,42 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
         const bool keep = off >= pre;                                  // pre is a multiple of the stage
         double s3 = 0.0;
         unsigned skip = 0u;
+        const double* lvs = lvbuf + (h & 1) * (2 * kTmMaxLeafOps * SC);
         if (LV) {
-            // the leaves of the fused programs depend on the frame only: every lane evaluates a few frames of the
-            // stage (the interpreter's exact formulas), all 32 rows then read them back as broadcasts
-            __syncwarp();
-            // (measured on config 5: replacing the per-frame sin() of the generators by angle additions across
-            //  stages does not change the run time — the kernel is bound by the FP64 dependency chains of the
-            //  cascade, not by these 6 evaluations per lane and stage — so the exact formulas stay)
-            for (int jj = 0; jj < P.n_in_ops + P.n_ep_ops; ++jj) {
+            // the leaves of the fused programs: every thread of the block evaluates at most a few values of the stage
+            // (the interpreter's exact per-frame formulas), all rows then read them back as broadcasts.  One block
+            // barrier per stage: the buffer written now was last read two stages ago, before the previous barrier.
+            double* lvw = lvbuf + (h & 1) * (2 * kTmMaxLeafOps * SC);
+            const int nops = P.n_in_ops + P.n_ep_ops;
+            const int64_t n0 = start + off;
+            unsigned ones = 0u;                                        // ramps are 1 outside a short region
+            for (int jj = 0; jj < nops; ++jj) {
                 const int j = jj < P.n_in_ops ? jj : kTmMaxLeafOps + jj - P.n_in_ops;
                 const sigops_instr* I = &P.ops[j];
-                const int64_t n0 = start + off;
-                bool ones = false;                                     // ramps are 1 outside a short region
-                if (I->leaf == SIGOPS_LEAF_RAMP_ON) ones = n0 + I->i0 > I->i1;
-                else if (I->leaf == SIGOPS_LEAF_RAMP_OFF) ones = n0 + (SC - 1) + I->i0 <= I->i1;
-                if (ones && (I->op == SIGOPS_OP_MUL || I->op == SIGOPS_OP_DIV)) {
-                    skip |= 1u << j;
-                    continue;
+                bool one = false;
+                if (I->leaf == SIGOPS_LEAF_RAMP_ON) one = n0 + I->i0 > I->i1;
+                else if (I->leaf == SIGOPS_LEAF_RAMP_OFF) one = n0 + (SC - 1) + I->i0 <= I->i1;
+                if (one) {
+                    ones |= 1u << j;
+                    if (I->op == SIGOPS_OP_MUL || I->op == SIGOPS_OP_DIV) skip |= 1u << j;
                 }
-                for (int fr = lane; fr < SC; fr += 32) lvbuf[j * SC + fr] = ones ? 1.0 : rowinv_leaf(I, n0 + fr);
             }
-            __syncwarp();
+            for (int v = threadIdx.x; v < nops * SC; v += NW * 32) {
+                const int jj = v / SC, fr = v - jj * SC;
+                const int j = jj < P.n_in_ops ? jj : kTmMaxLeafOps + jj - P.n_in_ops;
+                if ((skip >> j) & 1u) continue;
+                lvw[j * SC + fr] = ((ones >> j) & 1u) ? 1.0 : rowinv_leaf(&P.ops[j], n0 + fr);
+            }
+            __syncthreads();
         }
+        if (!active) continue;
 #pragma unroll
         for (int s = 0; s < SUBS; ++s) {
 #pragma unroll
             for (int blk = 0; blk < SUB / 16; ++blk) {
                 const int64_t rem = work - off - s * SUB - blk * 16;   // outputs of this block that exist
                 s3 += cascade16_swz<M, UNITB, T, LV>(f, rowp + s * 128, (SUBS * lane + s) & 7, blk, P.gain, P.scale, P.scale2,
-                                                     rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0), want_ss, &P, lvbuf + s * SUB + blk * 16, SC, skip);
+                                                     rem >= 16 ? 16 : (rem > 0 ? (int)rem : 0), want_ss, &P, lvs + s * SUB + blk * 16, SC, skip);
             }
             if (s == 0 && h + NS - 1 < nstage) {
                 // the stage filtered one iteration ago went to a tensor store: once the TMA unit has
@@ -321,8 +341,8 @@ k_iir_tmap(const __grid_constant__ IirTmapParams P, const __grid_constant__ CUte
         }
         __syncwarp();
     }
-    if (lane == 0) bulk_wait_all();
-    if (P.sumsq_slot >= 0 && live) {
+    if (lane == 0 && active) bulk_wait_all();
+    if (P.sumsq_slot >= 0 && live && active) {
         const int64_t inst = row / P.nch;
         atomicAdd(P.scalars + (size_t)inst * P.nscalars + P.sumsq_slot, ss);
     }

@@ -1030,7 +1030,8 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                     int64_t bestL = 0;
                     for (int64_t j = Wst / stage_cols + 1; j <= jmax; j += std::max<int64_t>(1, jmax / 4096)) {
                         const int64_t L = j * stage_cols, cpr = (N + L - 1) / L;
-                        const int64_t blocks = (groups * cpr + nw - 1) / nw;
+                        // (fused programs: the warps of a block share a chunk, see k_iir_tmap)
+                        const int64_t blocks = rowinv ? cpr * ((groups + nw - 1) / nw) : (groups * cpr + nw - 1) / nw;
                         const int64_t waves = (blocks + dev.sm_count - 1) / dev.sm_count;
                         const double cost = (double)waves * ((double)L + (cpr > 1 ? (double)Wst : 0.0) + 600.0);
                         if (cost < best) { best = cost; bestL = L; }
@@ -1068,7 +1069,7 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                             for (int k = 0; k < 5; ++k) T.coef[j][k] = tc[j * 5 + k];
                         const int M_ = s.iir.M;
                         const bool unitb = s.iir.unitb;
-                        dim3 tgrid((unsigned)((T.nunits + nw - 1) / nw));
+                        dim3 tgrid((unsigned)(rowinv ? T.cpr * ((groups + nw - 1) / nw) : (T.nunits + nw - 1) / nw));
                         if (getenv("SIGOPS_DEBUG"))
                             fprintf(stderr, "[sigops] IIR stage %zu: tensor-map%s rows=%lld N=%lld M=%d W=%lld L=%lld chunks/row=%lld blocks=%u\n", si,
                                     f32 ? " (Float32)" : (rowinv ? " (fused row-invariant programs)" : ""),
