@@ -5,11 +5,7 @@ mkdir -p gpurun_out
 timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_launches_bench.csv \
     python bench.py --steps 2 --warmup 1 --ninst 256 --e2e-ninst 32 > gpurun_out/r2_bench_under_ncu.log 2>&1
 # full captures of the dominant kernels
-timeout -k 10 300 ncu --set full --clock-control none --import-source on -k regex:k_fir_tmap -s 2 -c 1 -o gpurun_out/r2_fir_tmap python tools/profile_step.py cfg3 3 > /dev/null 2>&1
-timeout -k 10 300 ncu --set full --clock-control none --import-source on -k regex:k_iir_tmap -s 2 -c 1 -o gpurun_out/r2_iir_tmap_lv python tools/profile_step.py cfg5full 3 4 > /dev/null 2>&1
-timeout -k 10 300 ncu --set full --clock-control none --import-source on -k regex:k_iir_tmap -s 2 -c 1 -o gpurun_out/r2_iir_tmap python tools/profile_step.py cfg2 3 > /dev/null 2>&1
-timeout -k 10 300 ncu --set full --clock-control none --import-source on -k regex:k_map -s 8 -c 1 -o gpurun_out/r2_map python tools/profile_step.py cfg4 3 > /dev/null 2>&1
+timeout -k 10 300 ncu --set full --clock-control none --import-source on -k regex:k_fir_tmap -s 2 -c 1 -f -o gpurun_out/r2_fir_tmap python tools/profile_step.py cfg3 3 > /dev/null 2>&1
+timeout -k 10 300 ncu --set full --clock-control none --import-source on -k regex:k_iir_tmap -s 2 -c 1 -f -o gpurun_out/r2_iir_tmap_lv python tools/profile_step.py cfg5full 3 4 > /dev/null 2>&1
+timeout -k 10 300 ncu --set full --clock-control none --import-source on -k regex:k_iir_tmap -s 2 -c 1 -f -o gpurun_out/r2_iir_tmap python tools/profile_step.py cfg2 3 > /dev/null 2>&1
 ls -la gpurun_out/r2_*.ncu-rep
-# sanitizer on the new kernels' tests (small cases)
-timeout -k 10 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_fir_mma.py tests/test_gpu_wav.py -m gpu -x -q -k "not one_minute" 2>&1 | tail -4
-timeout -k 10 600 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_fir_mma.py -m gpu -x -q -k "feeds_normpower or resample_matches" 2>&1 | tail -4
