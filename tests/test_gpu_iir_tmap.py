@@ -137,3 +137,23 @@ def test_fused_row_invariant_programs(gpu):
         assert np.max(np.abs(got[k][0] - ref[k][0])) <= 1e-11 * rms(ref[k][0])
     want, _ = oracle.sink(chain(xs[1]))
     assert np.max(np.abs(got[1][0] - want)) <= F64_TOL * rms(want)
+
+
+def test_fused_programs_ragged_row_groups(gpu):
+    """The warps of a block share one chunk of 8 consecutive row groups (the leaf vectors are evaluated once per block):
+    270 rows = 8 full groups + one group of 14 rows, so the second block runs with one partly filled warp and seven
+    idle ones that still take part in the block's barriers."""
+    from signalops import AffineSin, Bandpass, Mix, Ramp, Until, ms, s, sin, sink_batch
+    rng = np.random.default_rng(56)
+    xs = [rng.standard_normal((48000, 30)) for _ in range(9)]          # 270 rows, 0.5 s at 96 kHz
+
+    def chain(x):
+        am = Amplify(Signal(x, 96 * kHz), Signal(AffineSin(0.5, 0.5), ω=5 * Hz)) >> Until(0.5 * s)
+        return am >> Filt(Bandpass, 500 * Hz, 4 * kHz) >> Ramp(10 * ms) >> Mix(Signal(sin, ω=1 * kHz) >> Until(0.5 * s))
+
+    got = sink_batch([chain(x) for x in xs], gpu)
+    assert gpu.last_stats["launches"] == 1
+    for k in (0, 4, 8):
+        want, _ = oracle.sink(chain(xs[k]))
+        assert got[k][0].shape == want.shape
+        assert np.max(np.abs(got[k][0] - want)) <= F64_TOL * rms(want)
