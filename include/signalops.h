@@ -197,7 +197,10 @@ enum {
     SIGOPS_LEAF_RAMP_ON,    /* k=n+i0 (1-based); i1=L: k<=L ? fn((k-1)/L) : 1                 */
     SIGOPS_LEAF_RAMP_OFF,   /* k=n+i0; i1=n0, i2=L: k<=n0 ? 1 : fn(1-(k-n0)/L)                */
     SIGOPS_LEAF_RMS,        /* sqrt(scalar[buf]/d0)  (Normpower divisor, d0 = N*C)            */
-    SIGOPS_LEAF_STAGE       /* the value the enclosing IIR/FIR stage just computed at (n,c)   */
+    SIGOPS_LEAF_STAGE,      /* the value the enclosing IIR/FIR stage just computed at (n,c)   */
+    SIGOPS_LEAF_RANDN       /* `Signal(randn; rng)` (src/functions.jl:98-114) on the device: N(0,1) as a pure function
+                               of (seed = i1, stream = i2 + index of the instance in the call, frame k = n+i0, 1-based):
+                               Philox4x32-10 on counter (k-1)>>1, stream / key seed, Box-Muller, cos for odd k, sin for even */
 };
 
 /* pad modes of LEAF_BUF (flags bits 1..2), src/padding.jl:110-192 */

@@ -107,6 +107,8 @@ def _function_next(x, maxlen, skip, prev):
 
 def _function_frames(x, block, a, b):
     if isinstance(x.fn, G.RandFn):
+        if hasattr(x.fn.rng, "frames"):          # counter-based stream (PhiloxRNG): a function of the frame index
+            return x.fn.rng.frames(a + 1 + block.offset, b + 1 + block.offset).reshape(-1, 1)
         return x.fn.rng.standard_normal(b - a).reshape(-1, 1)
     i = np.arange(a + 1, b + 1, dtype=np.float64) + block.offset
     fs = x.framerate

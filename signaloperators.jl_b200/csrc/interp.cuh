@@ -28,6 +28,7 @@ struct BufRef {            // one buffer of one instance
 struct Env {
     const BufRef* bufs;        // [nbuf] for this instance (shared memory copy)
     const double* scalars;     // [nscalars] for this instance (global)
+    int64_t inst;              // index of the instance in the whole call (all waves, all devices): noise stream offset
 };
 
 __device__ __forceinline__ double load_elem(const void* p, int dtype, int64_t i) {
@@ -68,11 +69,34 @@ __device__ __forceinline__ double gen_value(const sigops_instr& I, int64_t k) {
     return apply_fn(I.fn, t + I.d2, I.d3, I.d4);
 }
 
+// `Signal(randn; rng)` on the device (src/functions.jl:98-114): frame k (1-based) of noise stream `stream` under `seed`, a
+// pure function of its arguments — Philox4x32-10 (Salmon et al., SC'11) on counter ((k-1)>>1, stream), key seed, then
+// Box-Muller: r cos(2 pi u2) for odd k, r sin(2 pi u2) for even k.  host/philox.py is the same function in numpy.
+static __device__ __noinline__ double randn_value(int64_t seed, int64_t stream, int64_t k) {
+    const uint64_t pair = (uint64_t)(k - 1) >> 1, st = (uint64_t)stream, sd = (uint64_t)seed;
+    uint32_t c0 = (uint32_t)pair, c1 = (uint32_t)(pair >> 32), c2 = (uint32_t)st, c3 = (uint32_t)(st >> 32);
+    uint32_t k0 = (uint32_t)sd, k1 = (uint32_t)(sd >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const double u1 = ((double)((((uint64_t)c1 << 32) | c0) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    const double u2 = ((double)((((uint64_t)c3 << 32) | c2) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    const double r = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    return r * ((k & 1) ? cs : sn);
+}
+
 // Per-frame evaluation of the leaves that have no vector fast path (padded / non-Float64
 // buffers, channel sums, non-sinusoidal generators, frames inside a ramp).  Deliberately not
 // inlined: the 64-bit divisions and libm calls in here would otherwise be replicated V times
 // at every call site and push the kernels out of the instruction cache.
-static __device__ __noinline__ double leaf_value_slow(const sigops_instr* Ip, const BufRef* bufs, int64_t n, int c) {
+static __device__ __noinline__ double leaf_value_slow(const sigops_instr* Ip, const BufRef* bufs, int64_t n, int c, int64_t inst = 0) {
     const sigops_instr& I = *Ip;
     switch (I.leaf) {
         case SIGOPS_LEAF_BUF: {
@@ -100,6 +124,8 @@ static __device__ __noinline__ double leaf_value_slow(const sigops_instr* Ip, co
         }
         case SIGOPS_LEAF_GEN:
             return gen_value(I, n + I.i0);
+        case SIGOPS_LEAF_RANDN:
+            return randn_value(I.i1, I.i2 + inst, n + I.i0);
         case SIGOPS_LEAF_RAMP_ON: {
             const int64_t k = n + I.i0;
             if (k > I.i1) return 1.0;
@@ -301,7 +327,7 @@ __device__ __forceinline__ void eval_program(const sigops_instr* sprog, const do
                         for (int j = 0; j < V; ++j) v[j] = 1.0;
                     } else {
 #pragma unroll
-                        for (int j = 0; j < V; ++j) v[j] = leaf_value_slow(&sprog[pc], env.bufs, n0 + j * nstride, c);
+                        for (int j = 0; j < V; ++j) v[j] = leaf_value_slow(&sprog[pc], env.bufs, n0 + j * nstride, c, env.inst);
                     }
                 }
             }

@@ -58,6 +58,7 @@ struct FirParams {
     const double* dpfb;        // or nullptr
     const int64_t* xi0;        // [ceil(n_out/T)*T], tail repeats the last entry
     const double* phi;
+    int64_t inst0;             // index of the wave's first instance in the whole call (noise streams)
 };
 
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src, int src_bytes) {
@@ -316,7 +317,7 @@ k_fir(const __grid_constant__ FirParams P) {
         const double2 yv = lane_on ? *reinterpret_cast<const double2*>(ys + (size_t)r * kFirYPitch + 2 * lane) : make_double2(0.0, 0.0);
         const int64_t m = m0 + 2 * lane;
         const BufRef* bufs = P.bufrefs + (size_t)inst * P.nbuf;
-        Env env{bufs, P.scalars + (size_t)inst * P.nscalars};
+        Env env{bufs, P.scalars + (size_t)inst * P.nscalars, P.inst0 + inst};
         for (int i = lane; i < P.epi_prog_len; i += 32) {
             const sigops_instr& I = sprog_epi[i];
             double v = 0.0;

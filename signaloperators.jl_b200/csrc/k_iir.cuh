@@ -58,6 +58,7 @@ struct IirParams {
     int n_epi_scale;
     double epi_scale[2];
     int carry_is_shift;        // FIX reads s_in[k] = state_zs[k-1] directly (no CARRY launch)
+    int64_t inst0;             // index of the wave's first instance in the whole call (noise streams)
 };
 
 enum { IIR_MAIN = 0, IIR_FIX = 1, IIR_WARM = 2 };
@@ -304,7 +305,7 @@ k_iir(const __grid_constant__ IirParams P) {
     const int inst = (int)(row / P.nch), c = (int)(row % P.nch);
 
     for (int i = threadIdx.x; i < P.nbuf; i += blockDim.x) sbufs[i] = P.bufrefs[(size_t)inst * P.nbuf + i];
-    Env env{sbufs, P.scalars + (size_t)inst * P.nscalars};
+    Env env{sbufs, P.scalars + (size_t)inst * P.nscalars, P.inst0 + inst};
     prepare_program(P.instrs + P.in_prog_start, P.in_prog_len, sprog_in, lc_in, lr_in, env, P.L);
     prepare_program(P.instrs + P.epi_prog_start, P.epi_prog_len, sprog_epi, lc_epi, lr_epi, env, P.L);
     __syncthreads();

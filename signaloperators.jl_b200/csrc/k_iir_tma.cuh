@@ -85,7 +85,7 @@ __device__ __forceinline__ double cascade16(Cascade<M>& f, double* p, double gai
     }
     if (PROG && T.in_len > 0) {
         double t[16];
-        Env env{nullptr, nullptr};
+        Env env{nullptr, nullptr, 0};
         eval_program<16>(T.in_prog, T.in_lc, T.in_rot, T.in_len, env, n0, 1, c, xr, t, nullptr, 0);
 #pragma unroll
         for (int k = 0; k < 16; ++k) xr[k] = t[k];
@@ -105,7 +105,7 @@ __device__ __forceinline__ double cascade16(Cascade<M>& f, double* p, double gai
     }
     if (PROG && T.ep_len > 0 && keep) {      // warm-up outputs are discarded: no epilogue
         double t[16];
-        Env env{nullptr, nullptr};
+        Env env{nullptr, nullptr, 0};
         eval_program<16>(T.ep_prog, T.ep_lc, T.ep_rot, T.ep_len, env, n0, 1, c, out, t, nullptr, 0);
 #pragma unroll
         for (int k = 0; k < 16; ++k) out[k] = t[k];
@@ -136,7 +136,7 @@ k_iir_tma(const __grid_constant__ IirTmaParams Q) {
     __shared__ double2 lr_in[PROG ? SIGOPS_MAX_PROG : 1], lr_ep[PROG ? SIGOPS_MAX_PROG : 1];
     TmaProg T{sp_in, lc_in, lr_in, PROG ? P.in_prog_len : 0, sp_ep, lc_ep, lr_ep, PROG ? P.epi_prog_len : 0};
     if (PROG) {
-        Env env0{nullptr, nullptr};
+        Env env0{nullptr, nullptr, 0};
         prepare_program(P.instrs + P.in_prog_start, P.in_prog_len, sp_in, lc_in, lr_in, env0, 1);
         prepare_program(P.instrs + P.epi_prog_start, P.epi_prog_len, sp_ep, lc_ep, lr_ep, env0, 1);
         __syncthreads();

@@ -34,6 +34,7 @@ struct MapParams {
     int out_buf, sumsq_slot, out_nch;
     int n_pieces;
     int passes;                     // 2048-frame passes per block (kMapPasses, or 1 for small launches)
+    int64_t inst0;                  // index of the wave's first instance in the whole call (noise streams)
     sigops_piece pieces[kMaxPieces];
     int tile_prefix[kMaxPieces + 1];
 };
@@ -59,7 +60,7 @@ k_map(const __grid_constant__ MapParams P) {
     if (c < pc.ch_start || c >= pc.ch_start + pc.ch_count) return;
 
     for (int i = threadIdx.x; i < P.nbuf; i += blockDim.x) sbufs[i] = P.bufrefs[(size_t)inst * P.nbuf + i];
-    Env env{sbufs, P.scalars + (size_t)inst * P.nscalars};
+    Env env{sbufs, P.scalars + (size_t)inst * P.nscalars, P.inst0 + inst};
     prepare_program(P.instrs + pc.prog_start, pc.prog_len, sprog, leafconst, leafrot, env, kMapThreads);
     __syncthreads();
 

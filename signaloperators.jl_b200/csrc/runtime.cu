@@ -112,6 +112,7 @@ struct Slot {
     std::vector<Prepared> cache_launches;
     uint64_t cache_plan = 0;      // plan uid
     int64_t cache_ninst = -1;
+    int64_t cache_inst0 = 0;      // (plans with noise leaves: the launches carry the wave's first instance index)
     std::vector<cudaEvent_t> prof_pool;
     std::vector<int> prof_kind;
     size_t prof_used = 0;
@@ -247,6 +248,7 @@ struct sigops_plan {
     std::vector<PlanDev> dev;
     int nbuf() const { return (int)bufs.size(); }
     int max_stack = 0;
+    bool has_randn = false;        // some program draws device noise (LEAF_RANDN): launches depend on the wave's first instance index
     uint64_t uid = 0;
 };
 
@@ -291,6 +293,7 @@ int program_stack_depth(const sigops_plan& p, int start, int len, bool allow_sta
                 case SIGOPS_LEAF_STAGE:
                     if (!allow_stage) fail(SIGOPS_ERR_INVALID, "%s: LEAF_STAGE outside an epilogue", what);
                     break;
+                case SIGOPS_LEAF_RANDN: break;
                 default: fail(SIGOPS_ERR_INVALID, "%s: bad leaf kind %d", what, I.leaf);
             }
         } else if (I.op == SIGOPS_OP_PUSH) {
@@ -424,7 +427,7 @@ void derive_iir(sigops_plan& p, StageRT& s, int idx) {
             for (int i = 0; i < len; ++i) {
                 const sigops_instr& I = p.instrs[start + i];
                 if (I.op > SIGOPS_OP_DIV) { if (I.op == SIGOPS_OP_PUSH) ok = false; continue; }   // no stack in this path
-                if (I.leaf == SIGOPS_LEAF_RMS || I.leaf == SIGOPS_LEAF_CHANSUM) ok = false;
+                if (I.leaf == SIGOPS_LEAF_RMS || I.leaf == SIGOPS_LEAF_CHANSUM || I.leaf == SIGOPS_LEAF_RANDN) ok = false;
                 if (I.leaf == SIGOPS_LEAF_BUF) {
                     if (!is_input) { ok = false; continue; }
                     ++nbuf_leaves;
@@ -679,6 +682,8 @@ void parse_plan(sigops_plan& p, const void* bytes, size_t nbytes) {
         } else
             fail(SIGOPS_ERR_INVALID, "%s: unknown kind %d", what, g.kind);
     }
+    for (const sigops_instr& I : p.instrs)
+        if (I.op >= SIGOPS_OP_LOAD && I.op <= SIGOPS_OP_DIV && I.leaf == SIGOPS_LEAF_RANDN) p.has_randn = true;
 }
 
 // ---- device-side plan constants -------------------------------------------------
@@ -806,6 +811,7 @@ struct WaveIO {
     int64_t ninst;
     const sigops_buffer* in;   // device pointers, [ninst][n_inputs]
     const sigops_buffer* out;  // [ninst][n_outputs]
+    int64_t inst0 = 0;         // index of the wave's first instance in the whole call (LEAF_RANDN streams)
 };
 
 size_t temp_bytes_per_instance(const sigops_plan& p) {
@@ -910,7 +916,7 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
         slot.graph = nullptr;
         slot.replays = 0;
     };
-    if (!table_changed && slot.cache_plan == p.uid && slot.cache_ninst == ninst) {
+    if (!table_changed && slot.cache_plan == p.uid && slot.cache_ninst == ninst && (!p.has_randn || slot.cache_inst0 == io.inst0)) {
         // Same plan on the same buffers again: from the second replay on, the scalar reset and every launch of
         // the wave go out as ONE cudaGraphLaunch (plans of several small stages are launch-latency bound).
         static const bool no_graph = getenv("SIGOPS_NO_GRAPH") != nullptr;
@@ -952,7 +958,7 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
         const sigops_stage& g = s.st;
         if (g.kind == SIGOPS_STAGE_MAP) {
             MapParams P{};
-            P.instrs = pd.instrs; P.bufrefs = d_refs; P.scalars = scalars;
+            P.instrs = pd.instrs; P.bufrefs = d_refs; P.scalars = scalars; P.inst0 = io.inst0;
             P.nbuf = nbuf; P.nscalars = nscal;
             P.out_buf = g.out_buf; P.sumsq_slot = g.sumsq_slot; P.out_nch = p.bufs[g.out_buf].nchannels;
             P.n_pieces = g.n_pieces;
@@ -1088,7 +1094,7 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                 c = choose_iir_chunking(s, rows, dev.sm_count);
             }
             IirParams P{};
-            P.instrs = pd.instrs; P.bufrefs = d_refs; P.scalars = scalars;
+            P.instrs = pd.instrs; P.bufrefs = d_refs; P.scalars = scalars; P.inst0 = io.inst0;
             P.nbuf = nbuf; P.nscalars = nscal;
             P.out_buf = g.out_buf; P.sumsq_slot = g.sumsq_slot;
             P.in_prog_start = g.in_prog_start; P.in_prog_len = g.in_prog_len;
@@ -1166,7 +1172,7 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
             if (g.n_out == 0) continue;
             const int64_t rows = ninst * g.nchannels;
             FirParams P{};
-            P.instrs = pd.instrs; P.bufrefs = d_refs; P.scalars = scalars;
+            P.instrs = pd.instrs; P.bufrefs = d_refs; P.scalars = scalars; P.inst0 = io.inst0;
             P.nbuf = nbuf; P.nscalars = nscal;
             P.out_buf = g.out_buf; P.sumsq_slot = g.sumsq_slot;
             P.in_buf = s.fir.in_buf; P.in_len = s.fir.in_len;
@@ -1413,6 +1419,7 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
     }
     slot.cache_plan = p.uid;
     slot.cache_ninst = ninst;
+    slot.cache_inst0 = io.inst0;
     return replay();
 }
 
@@ -1466,7 +1473,7 @@ int64_t run_device_resident(sigops_plan& p, int di, int64_t ninst, const sigops_
     int64_t launches = 0;
     for (int64_t i0 = 0; i0 < ninst; i0 += wave) {
         slot.arena.reset();
-        WaveIO io{std::min(wave, ninst - i0), in ? in + i0 * p.h.n_inputs : nullptr, out + i0 * p.h.n_outputs};
+        WaveIO io{std::min(wave, ninst - i0), in ? in + i0 * p.h.n_inputs : nullptr, out + i0 * p.h.n_outputs, i0};
         launches += enqueue_wave(p, di, slot, stream, io);
     }
     return launches;
@@ -1726,7 +1733,7 @@ void run_host_on_device(sigops_plan& p, int di, int64_t i_begin, int64_t i_end, 
             // ---- stages on the slot's stream (WAV-layout inputs are transposed / decoded first, outputs encoded last)
             CUDA_OK(cudaStreamWaitEvent(slot.stream, dev.ev_in[s], 0));
             for (auto& j : wav_in) launch_wav(false, j.P, slot.stream);
-            WaveIO io{w, din.data(), dout.data()};
+            WaveIO io{w, din.data(), dout.data(), i_begin + i0};
             res.launches += enqueue_wave(p, di, slot, slot.stream, io) + (int64_t)wav_in.size() + (int64_t)wav_out.size();
             for (auto& j : wav_out) launch_wav(true, j.P, slot.stream);
             CUDA_OK(cudaGetLastError());

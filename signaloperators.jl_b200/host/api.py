@@ -12,6 +12,7 @@ from .graph import (AddChannel, After, Amplify, Append, Extend, FadeTo, Filt, Fo
                     lastframe, mirror, nchannels, nframes, one, randn, reverse, sampletype, sin,
                     sinramp, zero)
 from .lowering import LoweringError
+from .philox import PhiloxRNG
 from .units import Hz, dB, deg, frames, kframes, kHz, ms, rad, s
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -212,7 +212,7 @@ def sink_batch(xs, to):
     constants) and differ only in the arrays they read."""
     if not xs:
         return []
-    plans = [Lowerer().build(x) for x in xs]
+    plans = [Lowerer(instance_index=k).build(x) for k, x in enumerate(xs)]
     ref = plans[0].tobytes()
     for k, p in enumerate(plans[1:], 1):
         if p.tobytes() != ref:

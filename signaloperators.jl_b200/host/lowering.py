@@ -23,6 +23,7 @@ import numpy as np
 
 from . import dspjl, graph as G
 from .functors import functor_code
+from .philox import PhiloxRNG
 from .wav import WavSignal
 
 # ---- constants mirrored from include/signalops.h -------------------------------
@@ -31,7 +32,7 @@ OP_LOAD, OP_ADD, OP_SUB, OP_MUL, OP_DIV = 1, 2, 3, 4, 5
 OP_PUSH, OP_POPADD, OP_POPSUB, OP_POPMUL, OP_POPDIV = 6, 7, 8, 9, 10
 OP_NEG, OP_CAST_F32, OP_CAST_I64 = 11, 12, 13
 LEAF_NONE, LEAF_CONST, LEAF_BUF, LEAF_CHANSUM, LEAF_GEN = 0, 1, 2, 3, 4
-LEAF_RAMP_ON, LEAF_RAMP_OFF, LEAF_RMS, LEAF_STAGE = 5, 6, 7, 8
+LEAF_RAMP_ON, LEAF_RAMP_OFF, LEAF_RMS, LEAF_STAGE, LEAF_RANDN = 5, 6, 7, 8, 9
 PAD_CONST, PAD_CYCLE, PAD_MIRROR, PAD_LAST = 0, 1, 2, 3
 FLAG_HAS_OMEGA = 1
 FN_SIN, FN_COS, FN_SAW, FN_AFFINE_SIN, FN_AFFINE_COS, FN_IDENTITY, FN_SINRAMP = 1, 2, 3, 4, 5, 6, 7
@@ -229,7 +230,8 @@ def _intersect(a: Piece, b: Piece):
 
 
 class Lowerer:
-    def __init__(self):
+    def __init__(self, instance_index=0):
+        self.instance_index = instance_index     # position of this graph in a batch call (device noise streams)
         self.plan = Plan()
         self._input_ids = {}      # id(ndarray) -> input index
         self._barrier_memo = {}   # id(node) -> (buf tag, frames materialised, stage)
@@ -375,6 +377,14 @@ class Lowerer:
         fs = x.framerate
         if fs is None:
             raise G.SignalError("Unknown frame rate for a function signal.")
+        if isinstance(x.fn, G.RandFn) and isinstance(x.fn.rng, PhiloxRNG):
+            # device noise (src/functions.jl:98-114 with a counter-based generator): frame k of stream
+            # `stream base + index of the instance in the call`; the base makes the graphs of a batch (streams
+            # s, s+1, ...) lower to the same bytes
+            rng = x.fn.rng
+            seed = rng.seed - (1 << 64) if rng.seed >= (1 << 63) else rng.seed
+            return [Piece(lo, hi, clo, chi, [Instr(OP_LOAD, LEAF_RANDN, i0=shift + 1, i1=seed,
+                                                   i2=rng.stream - self.instance_index)])]
         code = None if isinstance(x.fn, G.RandFn) else functor_code(x.fn)
         if code is not None and x.nchannels == 1:
             fn, a, b = code
@@ -843,6 +853,8 @@ def host_function_frames(x, k_lo, k_hi):
     cannot express (arbitrary callables, `randn`)."""
     n = k_hi - k_lo
     if isinstance(x.fn, G.RandFn):
+        if hasattr(x.fn.rng, "frames"):
+            return x.fn.rng.frames(k_lo, k_hi).reshape(-1, 1)
         return x.fn.rng.standard_normal(n).reshape(-1, 1)
     k = np.arange(k_lo, k_hi, dtype=np.float64)
     t = k / x.framerate

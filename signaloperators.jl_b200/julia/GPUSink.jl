@@ -22,6 +22,7 @@ using SignalOperators: AbstractSignal, CutApply, PaddedSignal, AppendSignals, Fi
     process_sink_params, initsink, refineroot, root, resolvelen, child, sinramp, inflen,
     isknowninf, cycle, mirror, lastframe
 using DSP
+using Random
 
 export GPUSink, Sawtooth, AffineSin, AffineCos, lower
 
@@ -138,7 +139,7 @@ end
 # Additive API: a batch of structurally identical graphs = one plan, many instances.
 function SignalOperators.sink(xs::AbstractVector, to::GPUSink)
     xs = process_sink_params.(xs)
-    plans = lower.(xs)
+    plans = [lower(x; instance_index = i - 1) for (i, x) in enumerate(xs)]
     all(p -> p.bytes == plans[1].bytes, plans) || error("batch elements do not lower to the same plan")
     results = [pinned_matrix(to, p.outtype, nframes(x), nchannels(x)) for (x, p) in zip(xs, plans)]
     (isempty(xs) || nframes(xs[1]) == 0) || run!(to, plans, results)
@@ -208,7 +209,7 @@ const OP_LOAD, OP_ADD, OP_SUB, OP_MUL, OP_DIV = UInt8(1), UInt8(2), UInt8(3), UI
 const OP_PUSH, OP_POPADD, OP_POPSUB, OP_POPMUL, OP_POPDIV = UInt8(6), UInt8(7), UInt8(8), UInt8(9), UInt8(10)
 const OP_NEG, OP_CAST_F32, OP_CAST_I64 = UInt8(11), UInt8(12), UInt8(13)
 const LEAF_NONE, LEAF_CONST, LEAF_BUF, LEAF_CHANSUM, LEAF_GEN = UInt8(0), UInt8(1), UInt8(2), UInt8(3), UInt8(4)
-const LEAF_RAMP_ON, LEAF_RAMP_OFF, LEAF_RMS, LEAF_STAGE = UInt8(5), UInt8(6), UInt8(7), UInt8(8)
+const LEAF_RAMP_ON, LEAF_RAMP_OFF, LEAF_RMS, LEAF_STAGE, LEAF_RANDN = UInt8(5), UInt8(6), UInt8(7), UInt8(8), UInt8(9)
 const PAD_CONST, PAD_CYCLE, PAD_MIRROR, PAD_LAST = 0, 1, 2, 3
 const FLAG_HAS_OMEGA = UInt8(1)
 const FN_SIN, FN_COS, FN_SAW, FN_AFFINE_SIN, FN_AFFINE_COS, FN_IDENTITY, FN_SINRAMP =
@@ -307,8 +308,41 @@ mutable struct Lowerer
     stages::Vector{Stage}
     input_ids::Dict{UInt,Int}
     memo::Dict{Any,Any}
-    Lowerer() = new(BufDesc[], Array[], BufDesc[], BufDesc[], 0, Vector{Float64}[], Stage[], Dict{UInt,Int}(), Dict{Any,Any}())
+    instance_index::Int          # position of this graph in a batch call (device noise streams)
+    Lowerer(instance_index = 0) = new(BufDesc[], Array[], BufDesc[], BufDesc[], 0, Vector{Float64}[], Stage[], Dict{UInt,Int}(),
+                                      Dict{Any,Any}(), instance_index)
 end
+
+# `Signal(randn; rng = PhiloxRNG(seed, stream))`: noise drawn ON THE DEVICE (src/functions.jl:98-114 with a
+# counter-based generator).  Frame k of the stream is a pure function of (seed, stream, k) — Philox4x32-10 +
+# Box-Muller, host/philox.py is the executable definition — so nothing crosses the link and the numbers do not
+# depend on block scheduling.  In a batch, element i must carry stream = (stream of element 1) + i - 1.
+# On the CPU sink the object works as an AbstractRNG through `randn(rng)` (one draw per frame, in order).
+mutable struct PhiloxRNG <: Random.AbstractRNG
+    seed::UInt64
+    stream::Int64
+    pos::Int64                   # frames drawn so far by the CPU sink
+    PhiloxRNG(seed = 0, stream = 0) = new(UInt64(seed), Int64(stream), 0)
+end
+function philox4x32_10(c0::UInt32, c1::UInt32, c2::UInt32, c3::UInt32, k0::UInt32, k1::UInt32)
+    for _ in 1:10
+        p0, p1 = UInt64(0xD2511F53) * c0, UInt64(0xCD9E8D57) * c2
+        c0, c1, c2, c3 = ((p1 >> 32) % UInt32) ⊻ c1 ⊻ k0, p1 % UInt32, ((p0 >> 32) % UInt32) ⊻ c3 ⊻ k1, p0 % UInt32
+        k0 += 0x9E3779B9
+        k1 += 0xBB67AE85
+    end
+    c0, c1, c2, c3
+end
+function noiseframe(rng::PhiloxRNG, k::Integer)          # frame k (1-based) of the stream: host/philox.py `frames`
+    pair, st = UInt64(k - 1) >> 1, reinterpret(UInt64, rng.stream)
+    x0, x1, x2, x3 = philox4x32_10(pair % UInt32, (pair >> 32) % UInt32, st % UInt32, (st >> 32) % UInt32,
+                                   rng.seed % UInt32, (rng.seed >> 32) % UInt32)
+    unit(lo, hi) = (Float64(((UInt64(hi) << 32) | lo) >> 11) + 0.5) / 9007199254740992.0
+    u1, u2 = unit(x0, x1), unit(x2, x3)
+    r = sqrt(-2log(u1))
+    isodd(k) ? r * cospi(2u2) : r * sinpi(2u2)
+end
+Random.randn(rng::PhiloxRNG) = noiseframe(rng, rng.pos += 1)   # the CPU sink draws frame by frame, in order
 
 # ---- buffers (lowering.py `add_input` ... `new_scalar`) -------------------------------------------------------
 function add_input!(lw::Lowerer, arr::AbstractArray)
@@ -348,8 +382,8 @@ function intersect_pieces(a::Piece, b::Piece)
 end
 
 # ---- entry point (`Lowerer.build`) -------------------------------------------------------------------------------
-function lower(x; nframes = SignalOperators.nframes(x), outtype = nothing)
-    lw = Lowerer()
+function lower(x; nframes = SignalOperators.nframes(x), outtype = nothing, instance_index = 0)
+    lw = Lowerer(instance_index)
     N, C = Int(nframes), nchannels(x)
     S = sampletype(x)
     T = outtype !== nothing ? outtype : S <: Union{Integer,Bool} ? Int64 : S <: Union{Float32,Float64} ? S : Float64
@@ -380,6 +414,11 @@ function lower_node(lw, x::SignalFunction, shift, lo, hi, cm, co, clo, chi)     
     (lo >= hi || clo >= chi) && return Piece[]
     fs = framerate(x)
     ismissing(fs) && error("Unknown frame rate for a function signal.")
+    if x.fn isa RandFn && x.fn.rng isa PhiloxRNG
+        rng = x.fn.rng
+        return [Piece(lo, hi, clo, chi, [Instr(OP_LOAD, LEAF_RANDN; i0 = shift + 1, i1 = reinterpret(Int64, rng.seed),
+                                               i2 = rng.stream - lw.instance_index)])]
+    end
     code = x.fn isa RandFn ? nothing : functor_code(x.fn)
     if code !== nothing && nchannels(x) == 1
         fn, a, b = code

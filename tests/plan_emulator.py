@@ -100,6 +100,13 @@ class Emulator:
             return np.full(n.shape, math.sqrt(self.scalars[buf] / d0))
         if leaf == 8:
             return stage
+        if leaf == 9:                      # LEAF_RANDN: Philox noise, stream = i2 + index of the instance in the call
+            from signalops.philox import PhiloxRNG
+            k = n + i0
+            if k.size == 0:
+                return np.zeros(0)
+            assert np.all(np.diff(k) == 1)
+            return PhiloxRNG(i1, i2 + self.inst).frames(int(k[0]), int(k[-1]) + 1)
         raise ValueError(leaf)
 
     def run_prog(self, start, ln, n, c, stage=None):
@@ -123,7 +130,8 @@ class Emulator:
         return acc
 
     # ---- stages -----------------------------------------------------------------------
-    def run(self, inputs):
+    def run(self, inputs, inst=0):
+        self.inst = inst                  # index of this instance in the call (noise streams)
         self.bufs = [np.asarray(a).reshape(len(a), -1) for a in inputs]
         for k in range(self.n_in, len(self.bufdesc)):
             n, c, dt = self.bufdesc[k]

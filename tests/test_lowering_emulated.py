@@ -19,7 +19,7 @@ class _EmuPlan:
         n_in = len(ins) // ninst
         n_out = len(outs) // ninst
         for i in range(ninst):
-            res = Emulator(self.blob).run(ins[i * n_in:(i + 1) * n_in])
+            res = Emulator(self.blob).run(ins[i * n_in:(i + 1) * n_in], inst=i)
             for o, r in zip(outs[i * n_out:(i + 1) * n_out], res):
                 o.reshape(r.shape)[...] = r
         return {"launches": 0}
