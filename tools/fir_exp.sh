@@ -1,1 +1,4 @@
-timeout -k 10 600 python -m pytest tests/test_gpu_randn.py tests/test_gpu_iir_tmap.py -x -q -m gpu 2>&1 | tail -15
+timeout -k 10 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout -k 10 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
+python bench.py --steps 20 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json; echo "ref rc=$?"
