@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <future>
 #include <unordered_map>
 #include <memory>
 #include <mutex>
@@ -1627,7 +1628,7 @@ void run_host_on_device(sigops_plan& p, int di, int64_t i_begin, int64_t i_end, 
             if (!pinned_in) dev.stage_in[s].reserve(in_host * wave);
             if (!pinned_out) dev.stage_out[s].reserve(out_host * wave);
         }
-        struct InFlight { int64_t i0 = 0, w = 0; bool live = false; std::vector<CopyPiece> drain; };
+        struct InFlight { int64_t i0 = 0, w = 0; bool live = false; std::vector<CopyPiece> drain; std::future<void> drained; };
         InFlight fl[kHostSlots];
         // din/dout: the planar device buffers the stages see; c*_u / c*_d: what is copied (the same buffer, or for
         // a WAV-layout host buffer its raw interleaved bytes and a device scratch area next to the planar one)
@@ -1637,6 +1638,7 @@ void run_host_on_device(sigops_plan& p, int di, int64_t i_begin, int64_t i_end, 
         auto finish = [&](int s) {      // wave in staging buffer s: wait for its D2H, account, drain the pinned ring
             InFlight& f = fl[s];
             if (!f.live) return;
+            if (f.drained.valid()) f.drained.get();          // pageable results: the background drain of this buffer (rethrows)
             CUDA_OK(cudaEventSynchronize(dev.ev_out[s]));
             float ms = 0;
             cudaEventElapsedTime(&ms, dev.ev_t[s][0], dev.ev_t[s][1]); res.h2d_ms += ms;
@@ -1751,6 +1753,17 @@ void run_host_on_device(sigops_plan& p, int di, int64_t i_begin, int64_t i_end, 
             CUDA_OK(cudaEventRecord(dev.ev_t[s][3], dev.s_out));
             CUDA_OK(cudaEventRecord(dev.ev_out[s], dev.s_out));
             fl[s].i0 = i0; fl[s].w = w; fl[s].live = true;
+            if (!fl[s].drain.empty()) {
+                // pageable results leave the pinned ring on a background thread as soon as the wave's D2H has
+                // landed, while this thread stages the next waves' inputs: copy-in and copy-out of the caller's
+                // memory overlap instead of taking turns (the ring buffer is not touched again before finish(s))
+                fl[s].drained = std::async(std::launch::async, [&dev, s, nthreads, pieces = std::move(fl[s].drain)] {
+                    CUDA_OK(cudaSetDevice(dev.ordinal));
+                    CUDA_OK(cudaEventSynchronize(dev.ev_out[s]));
+                    parallel_copy(pieces, nthreads);
+                });
+                fl[s].drain.clear();
+            }
         }
         for (int j = 0; j < kHostSlots; ++j) finish((k + j) % kHostSlots);      // oldest first
     } catch (const Failure& f) {

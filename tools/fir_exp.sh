@@ -1,4 +1,7 @@
-timeout -k 10 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-timeout -k 10 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json; echo "ref rc=$?"
+timeout -k 10 600 python -m pytest tests/test_gpu_hostpath.py tests/test_gpu_wav.py tests/test_gpu_randn.py -x -q -m gpu 2>&1 | tail -3
+for t in 8 16; do
+  SIGOPS_COPY_THREADS=$t python bench.py --steps 3 --warmup 3 --ninst 128 --configs '' 2>/dev/null | grep '^{' | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); e=d['e2e']
+print('threads $t: pinned', round(e['value']), 'pageable', round(e['pageable']['value']), 'api', round(e['public_api']['value']))"
+done
