@@ -248,6 +248,17 @@ class Lowerer:
             m = m.astype(np.int64)
         elif m.dtype not in (np.float32, np.float64):
             m = m.astype(np.float64)
+        # numpy's own layout of an (nframes, nchannels) matrix is frame-interleaved — exactly a WAV data chunk, which the
+        # C ABI takes as it is (SIGOPS_INTERLEAVED: the device transposes).  No host-side transposition: numpy needs
+        # 45 ms for a one-minute stereo signal, eight times what the rest of the call costs
+        if m.ndim == 2 and m.shape[0] > 1 and m.shape[1] > 1 and m.flags.c_contiguous and m.dtype in (np.float32, np.float64):
+            from .wav import WavRaw
+            k = len(self.plan.inputs)
+            self.plan.inputs.append(BufDesc(m.shape[0], m.shape[1], dtype_code(m.dtype)))
+            self.plan.input_arrays.append(WavRaw(m))
+            self._input_ids[key] = k
+            self._keepalive.append(arr)
+            return ("in", k)
         # strided views (x[::2], stereo[:,0] of a C-ordered array, x[::-1]) become dense copies here:
         # the C ABI only describes rows that are contiguous in time
         if m.shape[0] > 1 and m.strides[0] != m.itemsize:

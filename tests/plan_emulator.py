@@ -132,6 +132,10 @@ class Emulator:
     # ---- stages -----------------------------------------------------------------------
     def run(self, inputs, inst=0):
         self.inst = inst                  # index of this instance in the call (noise streams)
+        # (WavRaw inputs — frame-interleaved host buffers, also what a C-ordered numpy matrix is passed as — are decoded
+        #  the way the device's k_wav does: PCM16 / 32768, floats as they are)
+        inputs = [a.decode().astype(np.float32 if a.raw.dtype == np.float32 else np.float64) if hasattr(a, "raw") else a
+                  for a in inputs]
         self.bufs = [np.asarray(a).reshape(len(a), -1) for a in inputs]
         for k in range(self.n_in, len(self.bufdesc)):
             n, c, dt = self.bufdesc[k]

@@ -116,7 +116,7 @@ def test_fused_row_invariant_programs(gpu):
     import os
     from signalops import AffineSin, Bandpass, Mix, Ramp, Until, ms, s, sin, sink_batch
     rng = np.random.default_rng(55)
-    xs = [rng.standard_normal((96000, 32)) for _ in range(3)]          # 96 rows, 1 s at 96 kHz
+    xs = [np.asfortranarray(rng.standard_normal((96000, 32))) for _ in range(3)]   # 96 rows, 1 s at 96 kHz (column-major: no decode launch)
 
     def chain(x):
         am = Amplify(Signal(x, 96 * kHz), Signal(AffineSin(0.5, 0.5), ω=5 * Hz)) >> Until(1 * s)
@@ -145,7 +145,7 @@ def test_fused_programs_ragged_row_groups(gpu):
     idle ones that still take part in the block's barriers."""
     from signalops import AffineSin, Bandpass, Mix, Ramp, Until, ms, s, sin, sink_batch
     rng = np.random.default_rng(56)
-    xs = [rng.standard_normal((48000, 30)) for _ in range(9)]          # 270 rows, 0.5 s at 96 kHz
+    xs = [np.asfortranarray(rng.standard_normal((48000, 30))) for _ in range(9)]   # 270 rows, 0.5 s at 96 kHz
 
     def chain(x):
         am = Amplify(Signal(x, 96 * kHz), Signal(AffineSin(0.5, 0.5), ω=5 * Hz)) >> Until(0.5 * s)
