@@ -17,23 +17,24 @@
 //     the signal, past its end, and rows past the last one are zero-filled by the TMA unit —
 //     the history before the first sample and the reference's zero padding (src/filters.jl:240);
 //   * finished 32-output tiles are staged in shared memory (two 16-output swizzled boxes) and
-//     written with `cp.async.bulk.tensor.2d` stores (16 outputs x 64 rows each) by one store thread per row half (whole 128-byte lines;
-//     columns past n_out and rows past the last are clipped by the tensor bounds);
-//   * the compute warps do nothing but LDS + DMMA + 16 shared-memory stores per tile.  Shared-memory
-//     bandwidth is the co-critical resource (ncu on the first version: LSU wavefronts + TMA traffic busy 70 %
-//     of the time, tensor pipe 66 %), so the k axis is walked in ring-aligned blocks of 4 positions whose A
-//     fragments are shared by all four output groups of the tile.
+//     written with `cp.async.bulk.tensor.2d` stores (16 outputs x 64 rows each) by one store thread per row half
+//     (whole 128-byte lines; columns past n_out and rows past the last are clipped by the tensor bounds);
+//   * the compute warps do nothing but LDS + DMMA + 8 shared-memory stores per tile: a k-step (block of 4 window
+//     positions) is 9 LDS + 8 DMMA + a select and an add.  Shared memory is the co-critical resource (an m8n8k4
+//     DMMA takes 256 bytes of A operand per 16 tensor cycles; ncu: tensor pipe 74 % active, the shared-memory pipe
+//     about 70 %).
 // A fragment rows are taken in bit-reversed order (fragment row r -> signal row {0,4,2,6,1,5,3,7}[r])
 // which makes both the swizzled A-fragment loads (any position alignment) and the staging stores
 // bank-conflict free.  The tap bands live at pitch 8 with an XOR on the column index (conflict-free
-// B-fragment loads) and are merged by four helper warps ON THE TENSOR PIPE (see below).  A fused constant gain (`ToFramerate |> Amplify(c)` is one launch) is folded into
-// the staged banks: g*(sum h x) becomes sum (g h) x, a rounding-level difference.  Groups whose eight outputs span fewer positions skip
-// the last k-step (44.1 -> 48 kHz: 11.4 instead of 12 on average).
+// B-fragment loads) and are merged by four helper warps ON THE TENSOR PIPE (see below).  A fused constant gain
+// (`ToFramerate |> Amplify(c)` is one launch) is folded into the staged banks: g*(sum h x) becomes sum (g h) x, a
+// rounding-level difference.  A band starts at its group's own first window position; groups whose eight outputs
+// span fewer positions skip the last k-step (44.1 -> 48 kHz: 11.4 instead of 12 on average).
 //
 // Block = 16 warps in four warpgroups that re-balance their registers with setmaxnreg: 8 compute (two per
-// sub-partition; each 8/G row fragments x G output groups, 176 registers), 4 helpers (tap bands, one per
-// group), 1 producer (ring loads), 1 store.  Barriers: full[slot], done[tile&3] (compute warps), taps[tile&1],
-// stg_full / stg_free (staging hand-over).
+// sub-partition; each 8 row fragments = 64 rows x one output group, 176 registers), 4 helpers (tap bands, one per
+// group), 1 producer (ring loads), 2 store threads (one per row half).  Barriers: full[slot], done[tile&3] (compute
+// warps), taps[tile&1], stg_full / stg_free per row half (staging hand-over).
 //
 // Eligibility (host): Float64 in/out, every row of the wave at base + row*stride with 16-byte
 // aligned base and stride (one batch tensor, or the library's own staging), epilogue = none or
