@@ -406,8 +406,7 @@ k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtens
         // the compute warp on the same sub-partition (measured here: ~200 cycles per DFMA, 4500 cycles per tile
         // for one FMA per merged tap); DMMAs of another warp simply interleave, at 6 % more tensor work.
         // Operands are table look-ups and selects: no FP64 ALU instruction in this branch.  Whole band rows are
-        // written (zeros included) as 16-byte pairs.  Band row 0 sits at the group's first window position
-        // rounded down to a multiple of 4 ring positions, so that the compute warps can share A blocks.
+        // written (zeros included) as 16-byte pairs.  Band row 0 sits at the group's first window position.
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kFtRegsHelper));
         const int grp = warp - kFtNCW;
         const int kk = lane & 3, rr = lane >> 2;
