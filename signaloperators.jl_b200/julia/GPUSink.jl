@@ -24,7 +24,7 @@ using SignalOperators: AbstractSignal, CutApply, PaddedSignal, AppendSignals, Fi
 using DSP
 using Random
 
-export GPUSink, Sawtooth, AffineSin, AffineCos, lower
+export GPUSink, Sawtooth, AffineSin, AffineCos, PhiloxRNG, lower
 
 const libsignalops = "libsignalops_cuda"
 

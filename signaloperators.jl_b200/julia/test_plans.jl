@@ -9,12 +9,18 @@
 # coefficients, polyphase banks, and the gain / rate / phase0 fields of a stage) must agree to 1e-12.
 using Test, SignalOperators, SignalOperators.Units, DSP
 include(joinpath(@__DIR__, "GPUSink.jl"))
-using .GPUSinks: lower, Sawtooth, AffineSin
+using .GPUSinks: lower, Sawtooth, AffineSin, PhiloxRNG
 
 const PLANS = normpath(joinpath(@__DIR__, "..", "..", "tests", "golden", "plans"))
 Z(dims...) = zeros(dims...)
 
 graphs = Dict(
+    "noise" => () -> begin
+        x = Signal(sin, ω = 1kHz) |> Until(1s) |> Ramp |> Normpower |> Amplify(-20dB + 5dB)
+        y = Signal(randn, 44.1kHz, rng = PhiloxRNG(UInt64(2)^63 + 1983, 3)) |> After(0.5s) |> Until(1s) |>
+            Filt(Bandstop, 0.5kHz, 2kHz) |> Normpower |> Amplify(-20dB)
+        Mix(x, y)
+    end,
     "cfg1" => () -> begin
         x = Signal(sin, ω = 1kHz) |> Until(1s) |> Ramp |> Normpower |> Amplify(-20dB + 5dB)
         y = Signal(Z(44100), 44.1kHz) |> Until(1s) |> Filt(Bandstop, 0.5kHz, 2kHz) |> Normpower |> Amplify(-20dB)

@@ -17,8 +17,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(HERE))))
 
 from signalops import (AddChannel, AffineSin, After, Amplify, Append, Bandpass, Bandstop, Filt, Hz, Lowpass, Mix,  # noqa: E402
-                       Normpower, Pad, Ramp, RampOn, Sawtooth, SelectChannel, Signal, ToChannels, ToFramerate, Until,
-                       cycle, dB, frames, kHz, ms, s, sin, zero)
+                       Normpower, Pad, PhiloxRNG, Ramp, RampOn, Sawtooth, SelectChannel, Signal, ToChannels, ToFramerate,
+                       Until, cycle, dB, frames, kHz, ms, randn, s, sin, zero)
 from signalops.lowering import lower  # noqa: E402
 
 Z = np.zeros
@@ -70,7 +70,15 @@ def channels():
     return AddChannel(a >> SelectChannel(2), a >> ToChannels(1)) >> ToChannels(2) >> Amplify(2)
 
 
-CASES = {"cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg3_gain": cfg3_gain, "cfg4": cfg4, "cfg5": cfg5,
+def noise():
+    """README scene with the noise drawn on the device (LEAF_RANDN): seed with the top bit set, stream 3, skipped frames."""
+    x = Signal(sin, ω=1 * kHz) >> Until(1 * s) >> Ramp() >> Normpower >> Amplify(-20 * dB + 5 * dB)
+    y = (Signal(randn, 44.1 * kHz, rng=PhiloxRNG(2 ** 63 + 1983, 3)) >> After(0.5 * s) >> Until(1 * s)
+         >> Filt(Bandstop, 0.5 * kHz, 2 * kHz) >> Normpower >> Amplify(-20 * dB))
+    return Mix(x, y)
+
+
+CASES = {"noise": noise, "cfg1": cfg1, "cfg2": cfg2, "cfg3": cfg3, "cfg3_gain": cfg3_gain, "cfg4": cfg4, "cfg5": cfg5,
          "plumbing": plumbing, "channels": channels}
 
 
