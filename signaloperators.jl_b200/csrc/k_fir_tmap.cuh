@@ -74,6 +74,8 @@ struct FirTmParams {
     const double* alpha;    // [m] fractional phase
     int tab_doubles;
     double gain;            // folded into the taps
+    const double* bands_g;  // periodic resamplers: merged tap bands of one period, [period_tiles][4][ks][8] (host-built), or nullptr
+    int period_tiles;
     long long* dbg;         // optional [blocks][8] cycle counters (tuning aid, SIGOPS_FIR_DBG=1), or nullptr
     int exp;                // tuning experiments (SIGOPS_FIR_EXP bit mask; wrong results): 1 no staging stores, 2 no tensor
                             // stores, 4 no tap-band building, 8 no ring loads, 16 compute warps do not wait for bands / data
@@ -152,8 +154,9 @@ k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtens
         done_count = 0u;
         for (int i = 0; i < P.nslot; ++i) mbar_init(&bar_full[i], 1);
         for (int i = 0; i < 4; ++i) mbar_init(&bar_done[i], kFtNCW);
-        mbar_init(&bar_taps[0], kFtNAW * 32);
-        mbar_init(&bar_taps[1], kFtNAW * 32);
+        // (tap bands from the period table: the loader's arrive.expect_tx and its arrival once the window has landed)
+        mbar_init(&bar_taps[0], P.bands_g ? 2 : kFtNAW * 32);
+        mbar_init(&bar_taps[1], P.bands_g ? 2 : kFtNAW * 32);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_stg_full[i], kFtNCW / 2);
             mbar_init(&bar_stg_free[i], 1);
@@ -409,6 +412,35 @@ k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtens
         // written (zeros included) as 16-byte pairs.  Band row 0 sits at the group's first window position.
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kFtRegsHelper));
         const int grp = warp - kFtNCW;
+        if (P.bands_g) {
+            // ---------------- periodic resampler: the tile's four bands are one bulk copy out of the period table ----------------
+            // (L2-resident: 12 KB per tile).  No look-ups, no merge DMMAs, no helper traffic on the shared-memory pipe.
+            if (grp == 0 && lane == 0) {
+                const unsigned bytes = 4u * (unsigned)P.ks * 64u;
+                int64_t jwait = 0;
+                int jw_slot = 0;
+                unsigned jw_par = 0;
+                for (int64_t t = t0; t < t1; ++t) {
+                    const int64_t u = t - t0;
+                    const int s = (int)(u & 1);
+                    const int64_t hi = (__ldg(P.xi0 + t * kFmT + kFmT - 1) + 1 - pos_base + (kFtSlotPos - 1)) >> 4;
+                    if (u >= 2) mbar_wait(&bar_done[(u - 2) & 3], (unsigned)((u - 2) >> 2) & 1u);   // the buffer's last reader
+                    mbar_expect_tx(&bar_taps[s], bytes);
+                    const double* src = P.bands_g + (size_t)(t % P.period_tiles) * (bytes / 8);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     bands + (unsigned)s * band_tile),
+                                 "l"(src), "r"(bytes), "r"(smem_u32(&bar_taps[s]))
+                                 : "memory");
+                    while (jwait < hi && !(P.exp & 8)) {                                          // ... and the tile's window has landed
+                        mbar_wait(&bar_full[jw_slot], jw_par);
+                        ++jwait;
+                        if (++jw_slot == P.nslot) { jw_slot = 0; jw_par ^= 1u; }
+                    }
+                    mbar_arrive(&bar_taps[s]);
+                }
+            }
+            return;
+        }
         const int kk = lane & 3, rr = lane >> 2;
         const unsigned pf_tab = tabs, dpf_tab = tabs + 8u * P.tab_doubles;
         const bool has_d = P.dpfb != nullptr;

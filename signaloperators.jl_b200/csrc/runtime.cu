@@ -208,6 +208,7 @@ struct FirDerived {
     int64_t in_len = 0;
     bool epi_const = true;       // epilogue = none or LOAD STAGE (MUL CONST){1,2}: folded into the taps
     double epi_scale = 1.0;
+    int64_t period = 0;          // outputs after which index pattern and taps repeat (multiple of 32), 0 = they do not
 };
 
 struct StageRT {
@@ -225,6 +226,7 @@ struct PlanDev {               // device-resident constants of a plan
     std::vector<int32_t*> poff;
     std::vector<double*> alpha;
     std::unordered_map<uint64_t, double*> carry;   // (stage, chunk length) -> device copy of the L-step transition matrix
+    std::unordered_map<uint64_t, double*> bands;   // (stage, ks) -> merged tap bands of one period (k_fir_tmap)
 };
 
 }  // namespace
@@ -588,6 +590,28 @@ void derive_fir(sigops_plan& p, StageRT& s, int idx) {
         s.fir.poff[m] = (int32_t)(((int64_t)fl - 1) * st.taps_per_phase);
         s.fir.alpha[m] = s.fir.phi[m] - fl;
     }
+    // Period of the resampler (rational ratios, e.g. 44.1 <-> 48 kHz: 160 outputs per 147 inputs): the index pattern must
+    // repeat EXACTLY over the whole output and the phase to 1e-9 (the Float64 accumulator drifts by ~1e-13 and may sit on
+    // either side of an integer phase: the merged taps are continuous across it).  k_fir_tmap then reads the merged tap
+    // bands of one period from a table instead of rebuilding them for every tile.
+    s.fir.period = 0;
+    if (nout >= 128) {
+        const double nphi_ = (double)st.n_phases;
+        auto same = [&](int64_t m, int64_t P, int64_t dx) {
+            if (s.fir.xi0[m + P] - s.fir.xi0[m] != dx) return false;
+            const double d = std::fabs(s.fir.phi[m + P] - s.fir.phi[m]);
+            return d <= 1e-9 && std::floor(s.fir.phi[m]) >= 1.0 && s.fir.phi[m] < nphi_ + 1.0;
+        };
+        for (int64_t P = 32; P <= 8192 && 2 * P <= nout && !s.fir.period; P += 32) {
+            const int64_t dx = s.fir.xi0[P] - s.fir.xi0[0];
+            bool ok = true;
+            for (int64_t m = 0; m < std::min<int64_t>(nout - P, 2 * P) && ok; ++m) ok = same(m, P, dx);
+            if (!ok) continue;
+            for (int64_t m = 2 * P; m + P < nout && ok; ++m) ok = same(m, P, dx);
+            if (ok) s.fir.period = P;
+            else break;                        // repeats for two periods, then drifts apart: no exact period
+        }
+    }
     int64_t dpad = 0, span = 0;
     for (int64_t m = 0; m + kFirR - 1 < padded; ++m) dpad = std::max(dpad, s.fir.xi0[m + kFirR - 1] - s.fir.xi0[m]);
     for (int64_t m = 0; m < padded; m += kFirT) span = std::max(span, s.fir.xi0[m + kFirT - 1] - s.fir.xi0[m]);
@@ -733,6 +757,8 @@ void free_plan_dev(sigops_plan& p) {
         for (auto q : d.alpha) cudaFree(q);
         for (auto& kv : d.carry) cudaFree(kv.second);
         d.carry.clear();
+        for (auto& kv : d.bands) cudaFree(kv.second);
+        d.bands.clear();
         d.ready = false;
     }
 }
@@ -1217,8 +1243,46 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                 const bool has_d = P.dpfb != nullptr;
                 while (nslot > win_slots + 1 && fir_tm_smem_bytes(nslot, ks, (int)tabd_, has_d) > kFirTmSmemLimit) --nslot;
                 if (const char* e = getenv("SIGOPS_FIR_NSLOT")) nslot = std::max(win_slots + 1, std::min(kFtMaxSlots, atoi(e)));
+                // periodic resamplers: merged tap bands of one period, built once per plan and device ([tile][4 groups][ks][8],
+                // columns XOR-swizzled like the helpers write them, the constant-gain epilogue folded in); no banks in shared
+                // memory then, which buys one more ring slot
+                const double* bands_g = nullptr;
+                int period_tiles = 0;
+                if (s.fir.period > 0 && g.sumsq_slot < 0 && !getenv("SIGOPS_NO_FIR_BANDS")) {
+                    const uint64_t key = ((uint64_t)si << 16) | (uint64_t)ks;
+                    auto it = pd.bands.find(key);
+                    if (it == pd.bands.end()) {
+                        const int64_t Pp = s.fir.period;
+                        const double* hp = p.blob.data() + p.tables[g.pfb_table].offset;
+                        const double* hd = g.dpfb_table >= 0 ? p.blob.data() + p.tables[g.dpfb_table].offset : nullptr;
+                        std::vector<double> tab((size_t)(Pp / 8) * ks * 8, 0.0);
+                        for (int64_t m = 0; m < Pp; ++m) {
+                            const int64_t m0 = m & ~int64_t(7);
+                            const int n = (int)(m - m0), stn = (int)(s.fir.xi0[m] - s.fir.xi0[m0]);
+                            double* band = tab.data() + (size_t)(m0 / 8) * ks * 8;
+                            for (int t = 0; t < g.taps_per_phase && stn + t < ks; ++t) {
+                                const double pf = hp[s.fir.poff[m] + t] * s.fir.epi_scale;
+                                const double h = hd ? std::fma(hd[s.fir.poff[m] + t] * s.fir.epi_scale, s.fir.alpha[m], pf) : pf;
+                                const int k = stn + t;
+                                band[k * 8 + (n ^ (((k >> 1) & 1) << 2))] = h;
+                            }
+                        }
+                        double* dptr = nullptr;
+                        CUDA_OK(cudaMalloc(&dptr, tab.size() * sizeof(double)));
+                        CUDA_OK(cudaMemcpy(dptr, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+                        it = pd.bands.emplace(key, dptr).first;
+                    }
+                    bands_g = it->second;
+                    period_tiles = (int)(s.fir.period / kFmT);
+                }
+                const int64_t tabd_eff = bands_g ? 0 : tabd_;
+                if (bands_g) {
+                    nslot = kFtMaxSlots;
+                    while (nslot > win_slots + 1 && fir_tm_smem_bytes(nslot, ks, 0, has_d) > kFirTmSmemLimit) --nslot;
+                    if (const char* e = getenv("SIGOPS_FIR_NSLOT")) nslot = std::max(win_slots + 1, std::min(kFtMaxSlots, atoi(e)));
+                }
                 TensorMapBlob mi, mo;
-                if (ks <= kFtMaxKs && nslot >= win_slots + 1 && fir_tm_smem_bytes(nslot, ks, (int)tabd_, has_d) <= kFirTmSmemLimit &&
+                if (ks <= kFtMaxKs && nslot >= win_slots + 1 && fir_tm_smem_bytes(nslot, ks, (int)tabd_eff, has_d) <= kFirTmSmemLimit &&
                     uniform(s.fir.in_buf, bin, sin_) && uniform(g.out_buf, bout, sout) && s.fir.in_len >= 1 &&
                     tmap_encode_2d_f64(&mi, bin, s.fir.in_len, rows, sin_, kFtSlotPos, kFtRows) &&
                     tmap_encode_2d_f64(&mo, bout, g.n_out, rows, sout, 16, kFtRows / 2)) {
@@ -1227,7 +1291,8 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                     T.nrows = rows; T.n_out = g.n_out; T.tapsper = g.taps_per_phase; T.ks = ks; T.nslot = nslot;
                     T.ntiles = (g.n_out + kFmT - 1) / kFmT;
                     T.pfb = P.pfb; T.dpfb = P.dpfb; T.xi0 = P.xi0; T.poff = pd.poff[si]; T.alpha = pd.alpha[si];
-                    T.tab_doubles = (int)tabd_;
+                    T.tab_doubles = (int)tabd_eff;
+                    T.bands_g = bands_g; T.period_tiles = period_tiles;
                     T.gain = s.fir.epi_scale;
                     if (const char* e = getenv("SIGOPS_FIR_EXP")) T.exp = atoi(e);
                     const int64_t groups = (rows + kFtRows - 1) / kFtRows;
@@ -1246,13 +1311,13 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                     if (const char* e = getenv("SIGOPS_FIR_TPS")) best_tps = std::max<int64_t>(1, atoll(e));
                     T.tiles_per_seg = best_tps;
                     const int64_t nseg = (T.ntiles + best_tps - 1) / best_tps;
-                    const size_t smem = fir_tm_smem_bytes(nslot, ks, (int)tabd_, has_d);
+                    const size_t smem = fir_tm_smem_bytes(nslot, ks, (int)tabd_eff, has_d);
                     dim3 tgrid((unsigned)nseg, (unsigned)groups);
                     if (groups <= 65535) {
                         if (getenv("SIGOPS_DEBUG"))
-                            fprintf(stderr, "[sigops] FIR stage %zu: tensor-map rows=%lld n_out=%lld taps=%d ks=%d slots=%d (window %d) grid=%lldx%lld tiles/seg=%lld smem=%zu gain=%g\n",
+                            fprintf(stderr, "[sigops] FIR stage %zu: tensor-map rows=%lld n_out=%lld taps=%d ks=%d slots=%d (window %d) grid=%lldx%lld tiles/seg=%lld smem=%zu gain=%g period=%lld outputs%s\n",
                                     si, (long long)rows, (long long)g.n_out, T.tapsper, ks, nslot, win_slots, (long long)nseg, (long long)groups,
-                                    (long long)best_tps, smem, T.gain);
+                                    (long long)best_tps, smem, T.gain, (long long)s.fir.period, bands_g ? " (tap bands from the period table)" : "");
                         const bool ssq = g.sumsq_slot >= 0;
                         if (getenv("SIGOPS_FIR_DBG")) {
                             // tuning aid: one synchronous launch with cycle counters, printed per role
