@@ -76,6 +76,8 @@ struct FirTmParams {
     double gain;            // folded into the taps
     const double* bands_g;  // periodic resamplers: merged tap bands of one period, [period_tiles][4][ks][8] (host-built), or nullptr
     int period_tiles;
+    int64_t epoch_tiles;    // one period table per epoch of this many tiles (the phase accumulator's drift), n_epochs of them
+    int n_epochs;
     long long* dbg;         // optional [blocks][8] cycle counters (tuning aid, SIGOPS_FIR_DBG=1), or nullptr
     int exp;                // tuning experiments (SIGOPS_FIR_EXP bit mask; wrong results): 1 no staging stores, 2 no tensor
                             // stores, 4 no tap-band building, 8 no ring loads, 16 compute warps do not wait for bands / data
@@ -426,7 +428,9 @@ k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtens
                     const int64_t hi = (__ldg(P.xi0 + t * kFmT + kFmT - 1) + 1 - pos_base + (kFtSlotPos - 1)) >> 4;
                     if (u >= 2) mbar_wait(&bar_done[(u - 2) & 3], (unsigned)((u - 2) >> 2) & 1u);   // the buffer's last reader
                     mbar_expect_tx(&bar_taps[s], bytes);
-                    const double* src = P.bands_g + (size_t)(t % P.period_tiles) * (bytes / 8);
+                    int64_t ep = t / P.epoch_tiles;
+                    ep = ep < P.n_epochs ? ep : P.n_epochs - 1;
+                    const double* src = P.bands_g + (size_t)(ep * P.period_tiles + t % P.period_tiles) * (bytes / 8);
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                                      bands + (unsigned)s * band_tile),
                                  "l"(src), "r"(bytes), "r"(smem_u32(&bar_taps[s]))

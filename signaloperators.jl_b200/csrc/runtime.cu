@@ -209,6 +209,8 @@ struct FirDerived {
     bool epi_const = true;       // epilogue = none or LOAD STAGE (MUL CONST){1,2}: folded into the taps
     double epi_scale = 1.0;
     int64_t period = 0;          // outputs after which index pattern and taps repeat (multiple of 32), 0 = they do not
+    int64_t epoch_tiles = 0;     // the Float64 phase accumulator drifts (linearly, ~1e-15 per output): the period table is
+    int64_t n_epochs = 0;        // rebuilt every epoch_tiles tiles so that the phase stays within 2e-10 of the table's
 };
 
 struct StageRT {
@@ -611,6 +613,30 @@ void derive_fir(sigops_plan& p, StageRT& s, int idx) {
             if (ok) s.fir.period = P;
             else break;                        // repeats for two periods, then drifts apart: no exact period
         }
+    }
+    if (s.fir.period) {
+        // Epochs: DSP.jl's accumulator `acc += delta` is reproduced step by step (parity with the reference includes
+        // its rounding drift: 4e-9 in phase over a one-minute signal, 1e-9 of the output).  One table per epoch, taken
+        // from the epoch's own first period, keeps the phase within 2e-10 of the table's (5e-11 of the output).
+        const int64_t P = s.fir.period, ptiles = P / 32, ntile = (nout + 31) / 32;
+        bool ok = false;
+        for (int64_t nep = 1; nep <= 4096 && !ok; nep *= 2) {
+            int64_t E = round_up((ntile + nep - 1) / nep, ptiles);
+            E = std::max(E, ptiles);
+            int64_t last = 0;                               // last epoch whose reference period lies inside the output
+            while ((last + 1) * E * 32 + P <= nout) ++last;
+            double worst = 0.0;
+            for (int64_t m = 0; m < nout; ++m) {
+                const int64_t e = std::min<int64_t>((m / 32) / E, last), start = e * E * 32;
+                worst = std::max(worst, std::fabs(s.fir.phi[m] - s.fir.phi[start + (m - start) % P]));
+            }
+            if (worst <= 2e-10) {
+                ok = true;
+                s.fir.epoch_tiles = E;
+                s.fir.n_epochs = last + 1;
+            }
+        }
+        if (!ok) s.fir.period = 0;
     }
     int64_t dpad = 0, span = 0;
     for (int64_t m = 0; m + kFirR - 1 < padded; ++m) dpad = std::max(dpad, s.fir.xi0[m + kFirR - 1] - s.fir.xi0[m]);
@@ -1248,23 +1274,28 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                 // memory then, which buys one more ring slot
                 const double* bands_g = nullptr;
                 int period_tiles = 0;
-                if (s.fir.period > 0 && g.sumsq_slot < 0 && !getenv("SIGOPS_NO_FIR_BANDS")) {
+                if (s.fir.period > 0 && g.sumsq_slot < 0 && !getenv("SIGOPS_NO_FIR_BANDS") &&
+                    (size_t)(s.fir.period / 8) * ks * 64 * (size_t)s.fir.n_epochs <= (size_t(96) << 20)) {
                     const uint64_t key = ((uint64_t)si << 16) | (uint64_t)ks;
                     auto it = pd.bands.find(key);
                     if (it == pd.bands.end()) {
                         const int64_t Pp = s.fir.period;
                         const double* hp = p.blob.data() + p.tables[g.pfb_table].offset;
                         const double* hd = g.dpfb_table >= 0 ? p.blob.data() + p.tables[g.dpfb_table].offset : nullptr;
-                        std::vector<double> tab((size_t)(Pp / 8) * ks * 8, 0.0);
-                        for (int64_t m = 0; m < Pp; ++m) {
-                            const int64_t m0 = m & ~int64_t(7);
-                            const int n = (int)(m - m0), stn = (int)(s.fir.xi0[m] - s.fir.xi0[m0]);
-                            double* band = tab.data() + (size_t)(m0 / 8) * ks * 8;
-                            for (int t = 0; t < g.taps_per_phase && stn + t < ks; ++t) {
-                                const double pf = hp[s.fir.poff[m] + t] * s.fir.epi_scale;
-                                const double h = hd ? std::fma(hd[s.fir.poff[m] + t] * s.fir.epi_scale, s.fir.alpha[m], pf) : pf;
-                                const int k = stn + t;
-                                band[k * 8 + (n ^ (((k >> 1) & 1) << 2))] = h;
+                        const size_t per_epoch = (size_t)(Pp / 8) * ks * 8;
+                        std::vector<double> tab(per_epoch * (size_t)s.fir.n_epochs, 0.0);
+                        for (int64_t e = 0; e < s.fir.n_epochs; ++e) {
+                            const int64_t start = e * s.fir.epoch_tiles * kFmT;          // the epoch's own first period
+                            for (int64_t q = 0; q < Pp; ++q) {
+                                const int64_t m = start + q, m0 = m & ~int64_t(7);
+                                const int n = (int)(m - m0), stn = (int)(s.fir.xi0[m] - s.fir.xi0[m0]);
+                                double* band = tab.data() + per_epoch * (size_t)e + (size_t)((q & ~int64_t(7)) / 8) * ks * 8;
+                                for (int t = 0; t < g.taps_per_phase && stn + t < ks; ++t) {
+                                    const double pf = hp[s.fir.poff[m] + t] * s.fir.epi_scale;
+                                    const double h = hd ? std::fma(hd[s.fir.poff[m] + t] * s.fir.epi_scale, s.fir.alpha[m], pf) : pf;
+                                    const int k = stn + t;
+                                    band[k * 8 + (n ^ (((k >> 1) & 1) << 2))] = h;
+                                }
                             }
                         }
                         double* dptr = nullptr;
@@ -1293,6 +1324,7 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                     T.pfb = P.pfb; T.dpfb = P.dpfb; T.xi0 = P.xi0; T.poff = pd.poff[si]; T.alpha = pd.alpha[si];
                     T.tab_doubles = (int)tabd_eff;
                     T.bands_g = bands_g; T.period_tiles = period_tiles;
+                    T.epoch_tiles = s.fir.epoch_tiles; T.n_epochs = (int)s.fir.n_epochs;
                     T.gain = s.fir.epi_scale;
                     if (const char* e = getenv("SIGOPS_FIR_EXP")) T.exp = atoi(e);
                     const int64_t groups = (rows + kFtRows - 1) / kFtRows;
@@ -1317,7 +1349,8 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                         if (getenv("SIGOPS_DEBUG"))
                             fprintf(stderr, "[sigops] FIR stage %zu: tensor-map rows=%lld n_out=%lld taps=%d ks=%d slots=%d (window %d) grid=%lldx%lld tiles/seg=%lld smem=%zu gain=%g period=%lld outputs%s\n",
                                     si, (long long)rows, (long long)g.n_out, T.tapsper, ks, nslot, win_slots, (long long)nseg, (long long)groups,
-                                    (long long)best_tps, smem, T.gain, (long long)s.fir.period, bands_g ? " (tap bands from the period table)" : "");
+                                    (long long)best_tps, smem, T.gain, (long long)s.fir.period, bands_g ? " (tap bands from the period tables)" : "");
+                            if (getenv("SIGOPS_DEBUG") && bands_g) fprintf(stderr, "[sigops]   %lld epochs of %lld tiles\n", (long long)s.fir.n_epochs, (long long)s.fir.epoch_tiles);
                         const bool ssq = g.sumsq_slot >= 0;
                         if (getenv("SIGOPS_FIR_DBG")) {
                             // tuning aid: one synchronous launch with cycle counters, printed per role

@@ -88,3 +88,37 @@ def test_resample_then_gain_is_one_launch(gpu):
     (y, _), = sink_batch([chain(xs[0])], gpu)
     assert gpu.last_stats["launches"] == 1
     assert float(np.max(np.abs(y.T - want[0])) / np.sqrt(np.mean(want[0] ** 2))) <= F64_TOL
+
+
+def test_period_table_and_rebuilt_bands_agree(gpu):
+    """A periodic resampler (44.1 -> 48 kHz: index pattern repeats every 160 outputs) reads its merged tap bands from a
+    host-built period table; SIGOPS_NO_FIR_BANDS=1 makes the helper warps rebuild them per tile from the polyphase banks.
+    Both must give the reference's result — they differ only where the drifting Float64 phase accumulator sits on either
+    side of an integer phase (continuous in the taps: ~1e-13)."""
+    rng = np.random.default_rng(21)
+    fi, fo, n_in = 44100.0, 48000.0, 200000
+    xs = [np.asfortranarray(rng.standard_normal((n_in, 2))) for _ in range(40)]       # 80 rows: tensor-map kernel
+    chain = lambda x: ToFramerate(Signal(x, fi * Hz), fo * Hz)                         # noqa: E731
+    a = sink_batch([chain(x) for x in xs], gpu)
+    b = with_env({"SIGOPS_NO_FIR_BANDS": "1"}, lambda: sink_batch([chain(x) for x in xs], gpu))
+    n_out = a[0][0].shape[0]
+    want = oracle_batch(np.stack([xs[k].T for k in (0, 39)]), fi, fo, n_out, threads=2)
+    for j, k in enumerate((0, 39)):
+        r = np.sqrt(np.mean(want[j] ** 2))
+        assert float(np.max(np.abs(a[k][0].T - want[j])) / r) <= F64_TOL
+        assert float(np.max(np.abs(b[k][0].T - want[j])) / r) <= F64_TOL
+        assert float(np.max(np.abs(a[k][0] - b[k][0])) / r) <= 1e-11
+
+
+def test_ratio_without_a_short_period_rebuilds_its_bands(gpu):
+    """44.1 kHz -> 47 999 Hz: no period within the table limit, so the general path (helper warps) serves the
+    tensor-map kernel; every sample against the oracle."""
+    rng = np.random.default_rng(22)
+    fi, fo, n_in = 44100.0, 47999.0, 150000
+    xs = [np.asfortranarray(rng.standard_normal((n_in, 2))) for _ in range(36)]       # 72 rows
+    got = sink_batch([ToFramerate(Signal(x, fi * Hz), fo * Hz) for x in xs], gpu)
+    n_out = got[0][0].shape[0]
+    want = oracle_batch(np.stack([xs[k].T for k in (0, 35)]), fi, fo, n_out, threads=2)
+    for j, k in enumerate((0, 35)):
+        assert got[k][1] == fo
+        assert float(np.max(np.abs(got[k][0].T - want[j])) / np.sqrt(np.mean(want[j] ** 2))) <= F64_TOL
