@@ -1,4 +1,9 @@
-timeout -k 10 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -3
-SIGOPS_DEBUG=1 timeout -k 10 120 python tools/profile_step.py cfg3 10 2>&1 | grep -E "epochs|cfg3:" | tail -2
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; tail -2 gpurun_out/bench_n1.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json; echo "ref rc=$?"
+#!/bin/bash
+# Ablations of the tensor-map FIR kernel on config 3 (64 signals); SIGOPS_FIR_EXP variants give wrong results by design
+# (bit mask: 1 no staging stores, 2 no tensor stores, 4 no tap-band building, 8 no ring loads, 16 no barrier waits).
+#   gpurun -- 'bash tools/fir_exp.sh'
+timeout -k 10 120 python tools/profile_step.py cfg3 10 2>&1 | tail -1
+echo "helper-built bands:"; SIGOPS_NO_FIR_BANDS=1 timeout -k 10 120 python tools/profile_step.py cfg3 10 2>&1 | tail -1
+for e in 4 8 7 31; do echo "SIGOPS_NO_FIR_BANDS=1 SIGOPS_FIR_EXP=$e"; SIGOPS_NO_FIR_BANDS=1 SIGOPS_FIR_EXP=$e timeout -k 10 120 python tools/profile_step.py cfg3 10 2>&1 | tail -1; done
+SIGOPS_NO_FIR_BANDS=1 SIGOPS_FIR_DBG=1 timeout -k 10 120 python tools/profile_step.py cfg3 2 2>&1 | grep "cycles/tile" | tail -1
+timeout -k 10 200 python tools/profile_step.py cfg3 10 1024 2>&1 | tail -1
