@@ -200,7 +200,9 @@ k_fir_mma(const __grid_constant__ FirMmaParams P) {
             if (wi >= P.ring) wi -= P.ring;
             have = need;
         };
-        auto need_of = [&](int64_t tile) { return (__ldg(P.xi0 + tile * kFmT + kFmT - 1) + 2) & ~int64_t(1); };
+        // (the k-steps of a group read ks positions from its window start: up to ks - tapsper past the window's end, times zero
+        //  taps — they must be landed data all the same, 0 * NaN is NaN)
+        auto need_of = [&](int64_t tile) { return (__ldg(P.xi0 + tile * kFmT + kFmT - 1) + 2 + (P.ks - P.tapsper)) & ~int64_t(1); };
 
         extend(need_of(t0), &bar_data[0]);              // the whole window of the first tile
         // index tables are read one tile ahead (they stream through L2 with everything else, so a

@@ -425,7 +425,9 @@ k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtens
                 for (int64_t t = t0; t < t1; ++t) {
                     const int64_t u = t - t0;
                     const int s = (int)(u & 1);
-                    const int64_t hi = (__ldg(P.xi0 + t * kFmT + kFmT - 1) + 1 - pos_base + (kFtSlotPos - 1)) >> 4;
+                    // (+ 4: the last block of a group reads up to 3 positions past its window — times zero taps, but what is
+                    //  multiplied must be landed data, not whatever the ring held: 0 * NaN is NaN)
+                    const int64_t hi = (__ldg(P.xi0 + t * kFmT + kFmT - 1) + 4 - pos_base + (kFtSlotPos - 1)) >> 4;
                     if (u >= 2) mbar_wait(&bar_done[(u - 2) & 3], (unsigned)((u - 2) >> 2) & 1u);   // the buffer's last reader
                     mbar_expect_tx(&bar_taps[s], bytes);
                     int64_t ep = t / P.epoch_tiles;
@@ -466,7 +468,7 @@ k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtens
             const bool live = m < P.n_out;
             const int po = po_nx;
             const double al = live ? al_nx : 0.0;
-            const int64_t hi = (xe_nx + 1 - pos_base + (kFtSlotPos - 1)) >> 4;     // slots [0, hi) hold the tile's window
+            const int64_t hi = (xe_nx + 4 - pos_base + (kFtSlotPos - 1)) >> 4;     // slots [0, hi) hold the tile's window (+ the 3 positions past it that the last blocks read, see band_loader)
             if (t + 1 < t1) {
                 xi_nx = __ldg(P.xi0 + m + kFmT);
                 po_nx = __ldg(P.poff + m + kFmT);
@@ -539,7 +541,7 @@ k_fir_tmap(const __grid_constant__ FirTmParams P, const __grid_constant__ CUtens
       if (warp == kFtNCW + kFtNAW) {
         // ---------------- producer: one tensor copy per ring slot, as far ahead as the ring allows ----------------
         if (lane == 0 && !(P.exp & 8)) {
-            const int64_t last_need = __ldg(P.xi0 + (t1 - 1) * kFmT + kFmT - 1) + 1;
+            const int64_t last_need = __ldg(P.xi0 + (t1 - 1) * kFmT + kFmT - 1) + 4;
             const int64_t nslots_total = (last_need - pos_base + (kFtSlotPos - 1)) >> 4;
             auto lo_of = [&](int64_t t) { return (__ldg(P.xi0 + t * kFmT) - P.tapsper + 1 - pos_base) >> 4; };
             int64_t tp = t0;

@@ -650,7 +650,8 @@ void derive_fir(sigops_plan& p, StageRT& s, int idx) {
     int64_t ring = 0;
     for (int64_t t = 0; t * kFmT < padded; ++t) {
         const int64_t tn = (t + 2) * kFmT <= padded ? t + 1 : t;      // loads run up to one tile ahead
-        const int64_t need = (s.fir.xi0[tn * kFmT + kFmT - 1] + 2) & ~int64_t(1);
+        const int64_t over = round_up(dpad + st.taps_per_phase, 4) - st.taps_per_phase;     // positions read past a window (zero taps)
+        const int64_t need = (s.fir.xi0[tn * kFmT + kFmT - 1] + 2 + over) & ~int64_t(1);
         const int64_t p0 = (s.fir.xi0[(t > 0 ? t - 1 : 0) * kFmT] - st.taps_per_phase + 1) & ~int64_t(1);
         ring = std::max(ring, need - p0);
     }
@@ -1264,7 +1265,7 @@ int64_t enqueue_wave(sigops_plan& p, int di, Slot& slot, cudaStream_t stream, co
                 int64_t sin_ = 0, sout = 0;
                 // a group's band starts at its first window position; the helpers build it in blocks of 8 rows
                 const int ks = (int)round_up(s.fir.dpad + g.taps_per_phase, 8);
-                const int win_slots = (s.fir.pmax32 + 14) / 16 + 1;          // worst alignment of a tile's window
+                const int win_slots = (s.fir.pmax32 + 3 + 14) / 16 + 1;      // worst alignment of a tile's window (+ 3 positions read past it)
                 int nslot = kFtMaxSlots;
                 const bool has_d = P.dpfb != nullptr;
                 while (nslot > win_slots + 1 && fir_tm_smem_bytes(nslot, ks, (int)tabd_, has_d) > kFirTmSmemLimit) --nslot;
