@@ -181,6 +181,10 @@ def sink_into(result, x, to):
     dense = _colmajor(result) is result
     if direct and dense:
         to.last_stats = cp.run_host(1, [_colmajor(a) for a in plan.input_arrays], [result])
+    elif (direct and result.ndim == 2 and result.shape[1] > 1 and result.flags.c_contiguous
+          and result.dtype in (np.float32, np.float64)):
+        # numpy's own (nframes, nchannels) layout is frame-interleaved: the device writes it directly (SIGOPS_INTERLEAVED)
+        to.last_stats = cp.run_host(1, [_colmajor(a) for a in plan.input_arrays], [WavRaw(result)])
     else:
         # strided / C-ordered / narrow-integer results: run into a dense temporary and copy back
         tmp = np.empty(result.shape, dtype=plan_dtype, order="F")

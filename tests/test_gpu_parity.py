@@ -422,3 +422,18 @@ def test_whole_frame_reverse(gpu):
     assert np.array_equal(got[0], np.stack([x[:, 1], x[:, 0]], axis=1))
     y = rng(45).random((50, 5))
     check(gpu, lambda: OperateOn(reverse, Signal(y, 10 * Hz), bychannel=False) >> Amplify(2), exact=True)
+
+
+def test_sink_into_c_ordered_result_in_place(gpu):
+    """`sink!` into numpy's own (nframes, nchannels) layout (src/sink.jl:158-168): written frame-interleaved by the device
+    (the WAV layout path, Float64 and Float32), no temporary on the host."""
+    x = rng(61).standard_normal((4000, 3))
+    for dt in (np.float64, np.float32):
+        sig = Signal(x.astype(dt), 48 * kHz) >> Filt(Lowpass, 4 * kHz) >> Amplify(-6 * dB)
+        res = np.full((3500, 3), np.nan, dtype=dt)
+        assert sink_into(res, sig, gpu) is res
+        want = np.empty((3500, 3), dtype=dt)
+        oracle.sink_into(want, sig)
+        tol = F64_TOL if dt == np.float64 else F32_TOL
+        assert not np.isnan(res).any()
+        assert np.max(np.abs(res.astype(np.float64) - want)) <= tol * rms(want)

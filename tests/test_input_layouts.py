@@ -50,3 +50,19 @@ def test_strided_views_become_dense_copies():
     ints = (rng.standard_normal((100, 2)) * 100).astype(np.int32)        # integers are widened to Int64 first
     (a,) = lower(Signal(ints, 48 * kHz)).input_arrays
     assert isinstance(a, np.ndarray) and a.dtype == np.int64
+
+
+def test_c_ordered_result_is_written_in_place():
+    """`sink!` into numpy's own (nframes, nchannels) layout: the device writes the frame-interleaved result directly."""
+    from signalops import sink_into
+    from test_lowering_emulated import EmulatedSink
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((3000, 2))
+    for dt in (np.float64, np.float32):
+        res = np.full((2500, 2), np.nan, dtype=dt)                       # C order
+        out = sink_into(res, chain(x.astype(dt)), EmulatedSink())
+        assert out is res and not np.isnan(res).any()
+        want = np.empty((2500, 2), dtype=dt)
+        oracle.sink_into(want, chain(x.astype(dt)))
+        tol = 1e-12 if dt == np.float64 else 1e-5
+        assert np.max(np.abs(res.astype(np.float64) - want)) <= tol * np.sqrt(np.mean(want.astype(np.float64) ** 2))

@@ -21,6 +21,7 @@ class _EmuPlan:
         for i in range(ninst):
             res = Emulator(self.blob).run(ins[i * n_in:(i + 1) * n_in], inst=i)
             for o, r in zip(outs[i * n_out:(i + 1) * n_out], res):
+                o = o.raw if hasattr(o, "raw") else o          # (WavRaw: a C-ordered result written in place)
                 o.reshape(r.shape)[...] = r
         return {"launches": 0}
 
